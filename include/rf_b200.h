@@ -1,0 +1,157 @@
+/* rf_b200.h — C ABI of librf_b200.so: the B200-native (sm_100a) FLUX.1-dev DiT hot path of
+ * Diffusion-CoT/ReflectionFlow.
+ *
+ * The reference has no FFI layer (it is pure Python over diffusers); its de-facto operator
+ * boundaries are Python callables.  Each entry point below names the reference interface it
+ * replaces (file:line under the reference tree).  Conventions:
+ *   - all tensor arguments are DEVICE pointers to contiguous bf16 unless stated otherwise;
+ *     token-major [tokens, channels] with an explicit row pitch in ELEMENTS where one is given
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call only
+ *     enqueues work on it — no hidden synchronisation, no allocation of caller-visible memory
+ *   - return value 0 = OK, negative = error; rf_last_error() returns a thread-local message
+ *   - a handle (rf_dit*) is bound to the CUDA device current at rf_dit_create and is not
+ *     thread-safe; weights are COPIED into handle-owned, kernel-friendly packed storage
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with an error
+ */
+#ifndef RF_B200_H_
+#define RF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RF_B200_ABI_VERSION 1
+
+/* error / version ------------------------------------------------------------------------- */
+const char* rf_last_error(void);
+int rf_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator level (what nn.Linear / SDPA / LayerNorm calls on the path dispatch to today).
+ * These are the units the parity tests exercise one by one.
+ * ---------------------------------------------------------------------------------------- */
+
+/* epilogue kinds of rf_op_linear */
+#define RF_EPI_BIAS 0     /* y = bf16(xW^T + b)                      nn.Linear                */
+#define RF_EPI_GELU 1     /* y = bf16(gelu_tanh(bf16(xW^T + b)))     FeedForward net[0], act_mlp
+                             (train_flux/flux/block.py:252,296)                               */
+#define RF_EPI_GATE_RES 2 /* y = bf16(res + bf16(gate * bf16(xW^T+b)))  gated residual
+                             (block.py:218-228,253-264,320-328)                               */
+#define RF_EPI_QKV 3      /* fused to_q|to_k|to_v: per-head RMSNorm(q,k) * w, interleaved RoPE
+                             (block.py:27-41,74-78,81-99)                                     */
+
+/* y[M,N] = epilogue(x[M,K] @ W[N,K]^T).  Replaces torch.nn.Linear.forward at every call site of
+ * train_flux/flux/block.py and transformer.py:92-93,115,244.  K % 64 == 0, N % 64 == 0.
+ * addend (nullable): [M,N] bf16 added after the bias rounding (peft LoRA B(A(x)) term,
+ * lora_controller.py:5-42).  RF_EPI_QKV: N = 3*heads*128, rope_cos/rope_sin are fp32 [M,64]
+ * pair-compact tables (diffusers FluxPosEmbed values at even channels), norm_q/norm_k bf16 [128]. */
+int rf_op_linear(int epilogue, int M, int N, int K, const void* x, int ldx, const void* W,
+                 const void* bias, void* y, int ldy, const void* addend, int ld_addend,
+                 const void* res, int ld_res, const void* gate, const float* rope_cos,
+                 const float* rope_sin, const void* norm_q, const void* norm_k, void* stream);
+
+/* O = softmax(Q K^T / sqrt(128)) V, non-causal, head_dim 128, token-major operands
+ * [batch*n_tok, heads*128] with row pitch ld_qkv / ld_out.  Replaces
+ * F.scaled_dot_product_attention at train_flux/flux/block.py:123-125 (plus the cat/transpose
+ * around it).  cond_mode: 0 = plain; 1 = additive bias `cond_bias` between tokens [0,n_main)
+ * and [n_main,n_tok) (attn.c_factor, block.py:115-122); 2 = those cross blocks masked out
+ * (union_cond_attn = False, block.py:106-114). */
+int rf_op_attention(const void* q, const void* k, const void* v, int ld_qkv, void* out, int ld_out,
+                    int n_tok, int heads, int batch, int n_main, int cond_mode, float cond_bias,
+                    void* stream);
+
+/* out = LayerNorm(x; no affine, eps 1e-6) * (1 + scale) + shift with the reference's bf16
+ * rounding after every op.  diffusers AdaLayerNormZero/ZeroSingle/Continuous body and
+ * block.py:232-247.  dim % 256 == 0, dim <= 3072.  Row r uses scale/shift + (r / rows_per_batch)
+ * * mod_stride. */
+int rf_op_ln_modulate(const void* x, int ldx, void* out, int ld_out, int rows, int dim,
+                      const void* scale, const void* shift, int rows_per_batch, int mod_stride,
+                      void* stream);
+
+/* y[b,n] = bf16(sum_k act(x[b,k]) W[n,k] + bias[n]); act 0 = identity, 1 = bf16(silu(x)).
+ * The adaLN `linear(silu(temb))` of every block and the timestep/guidance/text embedder MLPs
+ * (transformer.py:102-114).  K % 8 == 0, K <= 4096. */
+int rf_op_gemv(const void* x, int ldx, int batch, const void* W, const void* bias, void* y, int ldy,
+               int N, int K, int act, void* stream);
+
+/* diffusers Timesteps(256, flip_sin_to_cos=True, shift 0) of bf16(t * pre_scale) -> bf16 [batch,256]
+ * (transformer.py:95,98,102-114). */
+int rf_op_timestep_embed(const void* t, float pre_scale, void* out, int batch, void* stream);
+
+/* FlowMatchEulerDiscreteScheduler.step: x = bf16(float(x) + (sigmas[i+1]-sigmas[i]) * float(v))
+ * (generate.py:276).  sigmas: device fp32; step: device int32 index i. */
+int rf_op_euler_step(void* x, const void* v, const float* sigmas, const int* step, int n,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model level: the FLUX DiT forward and the denoise loop.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct rf_dit rf_dit;
+
+typedef struct rf_dit_config {
+  int num_layers;          /* double-stream blocks (FLUX.1-dev: 19) */
+  int num_single_layers;   /* single-stream blocks (38)             */
+  int num_heads;           /* 24; head_dim is fixed at 128          */
+  int in_channels;         /* 64                                    */
+  int joint_attention_dim; /* 4096 (T5 width)                       */
+  int pooled_projection_dim; /* 768 (CLIP pooled width)             */
+  int guidance_embeds;     /* 1 for FLUX.1-dev                      */
+  int lora_rank;           /* 0 = no LoRA storage; else rank (<= 64) of the condition LoRA */
+} rf_dit_config;
+
+int rf_dit_create(const rf_dit_config* cfg, rf_dit** out);
+void rf_dit_destroy(rf_dit* h);
+
+/* Copy one parameter into the handle.  `key` is the diffusers state-dict key of
+ * FluxTransformer2DModel (e.g. "transformer_blocks.3.attn.to_q.weight"); src is a DEVICE
+ * pointer to contiguous bf16 of `numel` elements.  Stands in for
+ * DiffusionPipeline.from_pretrained(...).to("cuda") (tts/tts_reflectionflow.py:498-501). */
+int rf_dit_load_weight(rf_dit* h, const char* key, const void* src, int64_t numel);
+
+/* peft LoRA factors of one target Linear (pipe.load_lora_weights, tts_reflectionflow.py:503-505;
+ * target list train_flux/config.yaml:53).  module = diffusers module path without ".weight"
+ * (e.g. "single_transformer_blocks.0.proj_out"); A: [r, in] bf16, B: [out, r] bf16 (device);
+ * scale = lora_alpha / r.  Applied to condition tokens only unless latent_lora is set in
+ * rf_dit_prepare (lora_controller.py:5-42). */
+int rf_dit_set_lora(rf_dit* h, const char* module, const void* A, const void* B, int r,
+                    float scale);
+
+/* Number of parameters still missing (0 = ready); names via rf_last_error(). */
+int rf_dit_missing_weights(rf_dit* h);
+
+/* Fix the problem geometry: token counts, position ids (bf16 [n,3], device), model_config flags.
+ * Builds the RoPE tables once (the reference rebuilds them every step, transformer.py:130-134)
+ * and sizes the workspace.  n_cond = 0 selects entry A (stock FluxTransformer2DModel.forward);
+ * n_cond > 0 selects entry B (train_flux/flux/transformer.py:47 tranformer_forward).
+ * flags: bit0 latent_lora, bit1 add_cond_attn, bit2 union_cond_attn==False;
+ * condition_scale != 1 enables the c_factor attention bias (generate.py:86-90). */
+int rf_dit_prepare(rf_dit* h, int batch, int n_txt, int n_img, int n_cond, const void* txt_ids,
+                   const void* img_ids, const void* cond_ids, int flags, float condition_scale,
+                   void* stream);
+
+/* One DiT forward == tranformer_forward(...)[0] / pipe.transformer(..., return_dict=False)[0].
+ *   latents [B,n_img,64]; txt [B,n_txt,4096] (T5 states); pooled [B,768];
+ *   timestep [B] bf16 (sigma, i.e. already / 1000 as generate.py:240 passes it);
+ *   guidance [B] fp32 (nullable when guidance_embeds == 0); cond_latents [B,n_cond,64] nullable;
+ *   out [B,n_img,64] bf16 noise prediction. */
+int rf_dit_forward(rf_dit* h, const void* latents, const void* txt, const void* pooled,
+                   const void* timestep, const float* guidance, const void* cond_latents,
+                   void* out, void* stream);
+
+/* The whole denoise loop of generate() / FluxPipeline.__call__ (generate.py:217-276):
+ * n_steps x (forward + Euler step), latents updated in place.  timesteps: HOST bf16 [n_steps]
+ * (the bf16(t)/1000 values the reference feeds), sigmas: HOST fp32 [n_steps+1].  The step body is
+ * captured once into a CUDA graph and replayed. */
+int rf_dit_denoise(rf_dit* h, void* latents_inout, const void* txt, const void* pooled,
+                   const uint16_t* timesteps_bf16_host, const float* sigmas_host, int n_steps,
+                   float guidance_scale, const void* cond_latents, void* stream);
+
+/* number of kernels this library launched since process start (for bench.py's gpu_launches) */
+int64_t rf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RF_B200_H_ */

@@ -1,0 +1,315 @@
+// elementwise.cu — the HBM-bound kernels of the DiT step (sm_100a).
+//
+//   ln_modulate   : LayerNorm(no affine, eps 1e-6) + adaLN scale/shift in one pass over the
+//                   hidden state; writes the bf16 A operand of the next GEMM.
+//                   (diffusers AdaLayerNormZero / ZeroSingle / Continuous bodies; reference call
+//                   sites train_flux/flux/block.py:186,191,201,232-247,295,299 and
+//                   transformer.py:243)
+//   gemv          : every adaLN modulation Linear of all 57 blocks in ONE launch per step
+//                   (M = batch <= 8 rows against ~1.06 M weight rows; pure weight streaming),
+//                   also the small time/guidance/text embedder MLPs (transformer.py:102-114)
+//   timestep_embed: sinusoidal projection (diffusers Timesteps(256, flip_sin_to_cos=True))
+//   euler_step    : FlowMatchEulerDiscreteScheduler.step (generate.py:276)
+// All of them keep the reference's bf16 rounding points.
+#include "rf_internal.h"
+#include "rf_ptx.cuh"
+
+namespace rf {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------- ln_modulate
+// one warp per row; dim <= 3072 and dim % 256 == 0 (each lane owns dim/256 16-byte chunks)
+static constexpr int kLnMaxChunks = 12;
+
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int ldo, int rows,
+                   int dim, const bf16* __restrict__ scale, const bf16* __restrict__ shift,
+                   int rows_per_batch, int mod_stride) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= rows) return;
+  const int row = warp_global;
+  const int b = row / rows_per_batch;
+  const int nch = dim >> 8;  // chunks per lane
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx);
+  float v[kLnMaxChunks][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i) {
+    if (i < nch) {
+      uint4 u = __ldg(xr + lane + 32 * i);
+      float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+             d = unpack_bf16x2(u.w);
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = bb.x; v[i][3] = bb.y;
+      v[i][4] = c.x; v[i][5] = c.y; v[i][6] = d.x; v[i][7] = d.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(dim);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i) {
+    if (i < nch) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = v[i][j] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+  const float var = warp_sum(sq) / static_cast<float>(dim);
+  const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(var + 1e-6f));
+  const uint4* sc = reinterpret_cast<const uint4*>(scale + static_cast<size_t>(b) * mod_stride);
+  const uint4* sh = reinterpret_cast<const uint4*>(shift + static_cast<size_t>(b) * mod_stride);
+  uint4* orow = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ldo);
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i) {
+    if (i < nch) {
+      uint4 us = __ldg(sc + lane + 32 * i), uh = __ldg(sh + lane + 32 * i);
+      uint32_t su[4] = {us.x, us.y, us.z, us.w};
+      uint32_t hu[4] = {uh.x, uh.y, uh.z, uh.w};
+      uint32_t ou[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 s2 = unpack_bf16x2(su[q]), h2 = unpack_bf16x2(hu[q]);
+        float y0 = bf16_round(__fmul_rn(v[i][2 * q] - mean, rstd));      // LayerNorm -> bf16
+        float y1 = bf16_round(__fmul_rn(v[i][2 * q + 1] - mean, rstd));
+        float t0 = bf16_round(1.0f + s2.x), t1 = bf16_round(1.0f + s2.y);  // (1 + scale) -> bf16
+        y0 = bf16_round(__fmul_rn(y0, t0));
+        y1 = bf16_round(__fmul_rn(y1, t1));
+        ou[q] = pack_bf16x2(y0 + h2.x, y1 + h2.y);                       // + shift -> bf16
+      }
+      orow[lane + 32 * i] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+    }
+  }
+}
+
+int ln_modulate_launch(const bf16* x, int ldx, bf16* out, int ldo, int rows, int dim,
+                       const bf16* scale, const bf16* shift, int rows_per_batch, int mod_stride,
+                       cudaStream_t stream) {
+  if (dim % 256 != 0 || dim > 256 * kLnMaxChunks || dim <= 0) {
+    set_error("ln_modulate: dim must be a multiple of 256, <= 3072");
+    return -1;
+  }
+  if (rows <= 0) return 0;
+  const int warps_per_block = 8;
+  const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  ln_modulate_kernel<<<blocks, 256, 0, stream>>>(x, ldx, out, ldo, rows, dim, scale, shift,
+                                                 rows_per_batch > 0 ? rows_per_batch : rows,
+                                                 mod_stride);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------- gemv
+// y[b, n] = bf16( sum_k act(x[b, k]) * W[n, k] + bias[n] ),  act = identity | bf16(silu)
+template <int NB>
+__global__ void __launch_bounds__(256)
+gemv_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ W,
+            const bf16* __restrict__ bias, bf16* __restrict__ y, int ldy, int N, int K, int act) {
+  extern __shared__ float xs[];  // [NB][K]
+  for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
+    const int b = i / K, k = i - b * K;
+    float v = __bfloat162float(x[static_cast<size_t>(b) * ldx + k]);
+    if (act == 1) v = bf16_round(__fdiv_rn(v, 1.0f + expf(-v)));  // silu in fp32 -> bf16
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int kchunks = K >> 3;  // 16-byte chunks per row
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps_total) {
+    const uint4* wr = reinterpret_cast<const uint4*>(W + static_cast<size_t>(n) * K);
+    float acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+    for (int c0 = lane; c0 < kchunks; c0 += 128) {
+      uint4 u[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c0 + 32 * q;
+        u[q] = (c < kchunks) ? __ldg(wr + c) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c0 + 32 * q;
+        if (c < kchunks) {
+          float2 w0 = unpack_bf16x2(u[q].x), w1 = unpack_bf16x2(u[q].y),
+                 w2 = unpack_bf16x2(u[q].z), w3 = unpack_bf16x2(u[q].w);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const float4* xp = reinterpret_cast<const float4*>(xs + b * K + c * 8);
+            float4 xa = xp[0], xb = xp[1];
+            acc[b] = fmaf(w0.x, xa.x, acc[b]); acc[b] = fmaf(w0.y, xa.y, acc[b]);
+            acc[b] = fmaf(w1.x, xa.z, acc[b]); acc[b] = fmaf(w1.y, xa.w, acc[b]);
+            acc[b] = fmaf(w2.x, xb.x, acc[b]); acc[b] = fmaf(w2.y, xb.y, acc[b]);
+            acc[b] = fmaf(w3.x, xb.z, acc[b]); acc[b] = fmaf(w3.y, xb.w, acc[b]);
+          }
+        }
+      }
+    }
+    const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float s = warp_sum(acc[b]);
+      if (lane == 0) y[static_cast<size_t>(b) * ldy + n] = __float2bfloat16_rn(s + bv);
+    }
+  }
+}
+
+template <int NB>
+static int gemv_launch_nb(const bf16* x, int ldx, const bf16* W, const bf16* bias, bf16* y,
+                          int ldy, int N, int K, int act, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(NB) * K * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       8 * 4096 * 4));
+    attr_set = true;
+  }
+  int blocks = (N + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  gemv_kernel<NB><<<blocks, 256, smem, stream>>>(x, ldx, W, bias, y, ldy, N, K, act);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int gemv_launch(const bf16* x, int ldx, int batch, const bf16* W, const bf16* bias, bf16* y,
+                int ldy, int N, int K, int act, cudaStream_t stream) {
+  if (K % 8 != 0 || K <= 0 || K > 4096) {
+    set_error("gemv: K must be a multiple of 8, <= 4096");
+    return -1;
+  }
+  int done = 0;
+  while (done < batch) {
+    const int left = batch - done;
+    const bf16* xb = x + static_cast<size_t>(done) * ldx;
+    bf16* yb = y + static_cast<size_t>(done) * ldy;
+    int rc, step;
+    if (left >= 8) { rc = gemv_launch_nb<8>(xb, ldx, W, bias, yb, ldy, N, K, act, stream); step = 8; }
+    else if (left >= 4) { rc = gemv_launch_nb<4>(xb, ldx, W, bias, yb, ldy, N, K, act, stream); step = 4; }
+    else if (left >= 2) { rc = gemv_launch_nb<2>(xb, ldx, W, bias, yb, ldy, N, K, act, stream); step = 2; }
+    else { rc = gemv_launch_nb<1>(xb, ldx, W, bias, yb, ldy, N, K, act, stream); step = 1; }
+    if (rc) return rc;
+    done += step;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------- timestep embedding
+// out[b, 0:128] = cos(t_b * f_i), out[b, 128:256] = sin(t_b * f_i), f_i = exp(-ln(1e4) * i / 128)
+// with t_b = bf16(t_in[b] * pre_scale) — the "* 1000" the reference applies in bf16
+// (train_flux/flux/transformer.py:95,98).
+__global__ void timestep_embed_kernel(const bf16* __restrict__ t, const int* __restrict__ step,
+                                      int t_stride, float pre_scale, bf16* __restrict__ out,
+                                      int batch) {
+  const int b = blockIdx.x;
+  const int i = threadIdx.x;  // 0..127
+  if (b >= batch || i >= 128) return;
+  const int idx = step ? *step : 0;
+  const float tv = bf16_round(__fmul_rn(__bfloat162float(t[static_cast<size_t>(b) * t_stride + idx]),
+                                        pre_scale));
+  const float expo = __fdiv_rn(__fmul_rn(-9.210340371976184f, static_cast<float>(i)), 128.0f);
+  const float f = expf(expo);
+  const float arg = __fmul_rn(tv, f);
+  out[static_cast<size_t>(b) * 256 + i] = __float2bfloat16_rn(cosf(arg));
+  out[static_cast<size_t>(b) * 256 + 128 + i] = __float2bfloat16_rn(sinf(arg));
+}
+
+int timestep_embed_launch(const bf16* t, const int* step, int t_stride, float pre_scale, bf16* out,
+                          int batch, cudaStream_t stream) {
+  timestep_embed_kernel<<<batch, 128, 0, stream>>>(t, step, t_stride, pre_scale, out, batch);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------- small elementwise
+__global__ void add3_kernel(const bf16* a, const bf16* b, const bf16* c, bf16* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = bf16_round(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+  out[i] = __float2bfloat16_rn(s + __bfloat162float(c[i]));
+}
+int add3_launch(const bf16* a, const bf16* b, const bf16* c, bf16* out, int n,
+                cudaStream_t stream) {
+  add3_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a, b, c, out, n);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// x_{i+1} = bf16( float(x_i) + (sigma_{i+1} - sigma_i) * float(v) )
+__global__ void euler_step_kernel(bf16* __restrict__ x, const bf16* __restrict__ v,
+                                  const float* __restrict__ sigmas, const int* __restrict__ step,
+                                  int n) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  const int s = *step;
+  const float dt = __fsub_rn(sigmas[s + 1], sigmas[s]);
+  uint4 ux = *reinterpret_cast<const uint4*>(x + i);
+  uint4 uv = __ldg(reinterpret_cast<const uint4*>(v + i));
+  uint32_t xs[4] = {ux.x, ux.y, ux.z, ux.w}, vs[4] = {uv.x, uv.y, uv.z, uv.w}, os[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float2 xf = unpack_bf16x2(xs[q]), vf = unpack_bf16x2(vs[q]);
+    os[q] = pack_bf16x2(__fadd_rn(xf.x, __fmul_rn(dt, vf.x)), __fadd_rn(xf.y, __fmul_rn(dt, vf.y)));
+  }
+  *reinterpret_cast<uint4*>(x + i) = make_uint4(os[0], os[1], os[2], os[3]);
+}
+int euler_step_launch(bf16* x, const bf16* v, const float* sigmas, const int* step, int n,
+                      cudaStream_t stream) {
+  if (n % 8 != 0) {
+    set_error("euler_step: n must be a multiple of 8");
+    return -1;
+  }
+  const int threads = n / 8;
+  euler_step_kernel<<<(threads + 255) / 256, 256, 0, stream>>>(x, v, sigmas, step, n);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+__global__ void advance_step_kernel(int* step) { *step += 1; }
+int advance_step_launch(int* step, cudaStream_t stream) {
+  advance_step_kernel<<<1, 1, 0, stream>>>(step);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+__global__ void copy_rows_kernel(const bf16* __restrict__ src, int lds, bf16* __restrict__ dst,
+                                 int ldd, int rows, int chunks_per_row) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(rows) * chunks_per_row;
+  if (idx >= total) return;
+  const int r = static_cast<int>(idx / chunks_per_row);
+  const int c = static_cast<int>(idx - static_cast<long long>(r) * chunks_per_row);
+  const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * lds) + c;
+  uint4* d = reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * ldd) + c;
+  *d = __ldg(s);
+}
+int copy_rows_launch(const bf16* src, int lds, bf16* dst, int ldd, int rows, int cols,
+                     cudaStream_t stream) {
+  if (cols % 8 != 0) {
+    set_error("copy_rows: cols must be a multiple of 8");
+    return -1;
+  }
+  const long long total = static_cast<long long>(rows) * (cols / 8);
+  if (total == 0) return 0;
+  copy_rows_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(src, lds, dst, ldd,
+                                                                             rows, cols / 8);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace rf

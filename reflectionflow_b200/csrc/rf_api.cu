@@ -1,0 +1,108 @@
+// rf_api.cu — operator-level C ABI (include/rf_b200.h) over the kernel launchers.
+#include <atomic>
+#include <cstring>
+
+#include "../../include/rf_b200.h"
+#include "rf_internal.h"
+
+namespace rf {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* get_error() { return g_err.c_str(); }
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+}  // namespace rf
+
+using rf::bf16;
+
+extern "C" {
+
+const char* rf_last_error(void) { return rf::get_error(); }
+int rf_abi_version(void) { return RF_B200_ABI_VERSION; }
+int64_t rf_launch_count(void) { return rf::launch_count(); }
+
+int rf_op_linear(int epilogue, int M, int N, int K, const void* x, int ldx, const void* W,
+                 const void* bias, void* y, int ldy, const void* addend, int ld_addend,
+                 const void* res, int ld_res, const void* gate, const float* rope_cos,
+                 const float* rope_sin, const void* norm_q, const void* norm_k, void* stream) {
+  if (!x || !W || !y) {
+    rf::set_error("rf_op_linear: null operand");
+    return -1;
+  }
+  rf::GemmGroupArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = static_cast<const bf16*>(x); g.lda = ldx; g.M = M;
+  g.W = static_cast<const bf16*>(W);
+  g.bias = static_cast<const bf16*>(bias);
+  g.out = static_cast<bf16*>(y); g.ldo = ldy;
+  g.addend = static_cast<const bf16*>(addend); g.ldadd = ld_addend;
+  g.res = static_cast<const bf16*>(res); g.ldr = ld_res;
+  g.gate = static_cast<const bf16*>(gate);
+  g.rope_cos = rope_cos; g.rope_sin = rope_sin;
+  g.norm_q = static_cast<const bf16*>(norm_q);
+  g.norm_k = static_cast<const bf16*>(norm_k);
+  return rf::gemm_launch(epilogue, N, K, 1, &g, static_cast<cudaStream_t>(stream));
+}
+
+int rf_op_attention(const void* q, const void* k, const void* v, int ld_qkv, void* out, int ld_out,
+                    int n_tok, int heads, int batch, int n_main, int cond_mode, float cond_bias,
+                    void* stream) {
+  if (!q || !k || !v || !out) {
+    rf::set_error("rf_op_attention: null operand");
+    return -1;
+  }
+  rf::AttnArgs a;
+  a.q = static_cast<const bf16*>(q); a.k = static_cast<const bf16*>(k);
+  a.v = static_cast<const bf16*>(v); a.ld_qkv = ld_qkv;
+  a.out = static_cast<bf16*>(out); a.ldo = ld_out;
+  a.n_tok = n_tok; a.heads = heads; a.batch = batch;
+  a.n_main = n_main; a.cond_mode = cond_mode; a.cond_bias = cond_bias;
+  return rf::attention_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+int rf_op_ln_modulate(const void* x, int ldx, void* out, int ld_out, int rows, int dim,
+                      const void* scale, const void* shift, int rows_per_batch, int mod_stride,
+                      void* stream) {
+  if (!x || !out || !scale || !shift) {
+    rf::set_error("rf_op_ln_modulate: null operand");
+    return -1;
+  }
+  return rf::ln_modulate_launch(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(out), ld_out,
+                                rows, dim, static_cast<const bf16*>(scale),
+                                static_cast<const bf16*>(shift), rows_per_batch, mod_stride,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int rf_op_gemv(const void* x, int ldx, int batch, const void* W, const void* bias, void* y, int ldy,
+               int N, int K, int act, void* stream) {
+  if (!x || !W || !y) {
+    rf::set_error("rf_op_gemv: null operand");
+    return -1;
+  }
+  return rf::gemv_launch(static_cast<const bf16*>(x), ldx, batch, static_cast<const bf16*>(W),
+                         static_cast<const bf16*>(bias), static_cast<bf16*>(y), ldy, N, K, act,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int rf_op_timestep_embed(const void* t, float pre_scale, void* out, int batch, void* stream) {
+  if (!t || !out) {
+    rf::set_error("rf_op_timestep_embed: null operand");
+    return -1;
+  }
+  return rf::timestep_embed_launch(static_cast<const bf16*>(t), nullptr, 1, pre_scale,
+                                   static_cast<bf16*>(out), batch,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int rf_op_euler_step(void* x, const void* v, const float* sigmas, const int* step, int n,
+                     void* stream) {
+  if (!x || !v || !sigmas || !step) {
+    rf::set_error("rf_op_euler_step: null operand");
+    return -1;
+  }
+  return rf::euler_step_launch(static_cast<bf16*>(x), static_cast<const bf16*>(v), sigmas, step, n,
+                               static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// rf_internal.h — host-side declarations shared by the kernel translation units and the
+// DiT orchestrator.  Nothing here is part of the public C ABI (see include/rf_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace rf {
+
+typedef __nv_bfloat16 bf16;
+
+// thread-local error string behind rf_last_error()
+void set_error(const std::string& msg);
+const char* get_error();
+// launch accounting behind rf_launch_count()
+void count_launch(int n = 1);
+int64_t launch_count();
+
+#define RF_CHECK_CUDA(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::rf::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+      return -2;                                                                         \
+    }                                                                                    \
+  } while (0)
+
+// Encode a 2-D bf16 row-major tensor map with 128-byte swizzle.
+//   rows x cols elements, row pitch ld (elements); box = box_rows x 64 columns.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols = 64);
+
+// ---------------------------------------------------------------------------- GEMM
+enum GemmEpilogue {
+  EPI_BIAS = 0,      // out = bf16(acc + bias)
+  EPI_GELU = 1,      // out = bf16(gelu_tanh(bf16(acc + bias)))
+  EPI_GATE_RES = 2,  // out = bf16(res + bf16(gate[n] * bf16(acc + bias)))
+  EPI_QKV = 3,       // q,k sections: per-head RMSNorm * w, interleaved RoPE; v: bias only
+};
+
+// One member of a grouped GEMM: out[M, N] = epi(A[M, K] @ W[N, K]^T).  All groups of a
+// launch share N, K and the epilogue kind; they differ in operands (token streams).
+struct GemmGroupArgs {
+  const bf16* A;   int lda;  int M;
+  const bf16* W;             // [N, K] row-major (torch Linear weight layout), ld = K
+  const bf16* bias;          // [N] or nullptr
+  bf16* out;       int ldo;
+  const bf16* addend; int ldadd;   // optional [M, N] term added after the bias rounding (LoRA)
+  const bf16* res; int ldr;        // EPI_GATE_RES
+  const bf16* gate;                // EPI_GATE_RES: [N]
+  const float* rope_cos;           // EPI_QKV: [M, 64] (pair-compact), row index local to group
+  const float* rope_sin;
+  const bf16* norm_q;              // EPI_QKV: [128]
+  const bf16* norm_k;
+};
+int gemm_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups,
+                cudaStream_t stream);
+
+// ---------------------------------------------------------------------------- attention
+// Non-causal softmax(Q K^T / sqrt(128)) V over one joint token sequence.
+// qkv: [n_tok, ld_qkv] with q at column 0, k at +q_stride... (see attn_sm100.cu)
+struct AttnArgs {
+  const bf16* q; const bf16* k; const bf16* v;  // each [n_tok, heads*128] slices, pitch ld_qkv
+  int ld_qkv;
+  bf16* out; int ldo;                           // [n_tok, heads*128], pitch ldo
+  int n_tok; int heads; int batch;              // rows of batch b start at b*n_tok
+  int n_main;                                   // tokens [0, n_main) vs [n_main, n_tok) = cond
+  int cond_mode;                                // 0 none, 1 additive log-bias, 2 block mask
+  float cond_bias;                              // log(c_factor) when cond_mode == 1
+};
+int attention_launch(const AttnArgs& a, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------- bandwidth kernels
+// out = bf16(bf16(bf16(LN(x)) * bf16(1 + scale)) + shift)   (LN: no affine, eps 1e-6)
+//   rows of batch element b (= row / rows_per_batch) use scale/shift + b * mod_stride
+int ln_modulate_launch(const bf16* x, int ldx, bf16* out, int ldo, int rows, int dim,
+                       const bf16* scale, const bf16* shift, int rows_per_batch, int mod_stride,
+                       cudaStream_t stream);
+// y[n] = bf16(sum_k act(x[k]) * W[n, k] + b[n]) for `batch` input vectors.
+//   act: 0 identity, 1 = bf16(silu(x))
+int gemv_launch(const bf16* x, int ldx, int batch, const bf16* W, const bf16* bias, bf16* y,
+                int ldy, int N, int K, int act, cudaStream_t stream);
+// sinusoidal timestep projection (256 channels, flip_sin_to_cos) of a bf16 scalar * 1000
+//   t value of batch b = t[b * t_stride + (step ? *step : 0)]
+int timestep_embed_launch(const bf16* t, const int* step, int t_stride, float pre_scale, bf16* out,
+                          int batch, cudaStream_t stream);
+int advance_step_launch(int* step, cudaStream_t stream);
+// out = bf16(a + b + c) evaluated left to right with bf16 rounding after each add
+int add3_launch(const bf16* a, const bf16* b, const bf16* c, bf16* out, int n,
+                cudaStream_t stream);
+// x = bf16(float(x) + dt * float(v))
+int euler_step_launch(bf16* x, const bf16* v, const float* sigmas, const int* step, int n,
+                      cudaStream_t stream);
+int copy_rows_launch(const bf16* src, int lds, bf16* dst, int ldd, int rows, int cols,
+                     cudaStream_t stream);
+
+}  // namespace rf
