@@ -609,7 +609,7 @@ def single_block(blk: FluxSingleTransformerBlock, prefix: str, lora: LoraSet, x,
 def transformer_forward(model: FluxTransformer2DModel, hidden_states, encoder_hidden_states,
                         pooled_projections, timestep, img_ids, txt_ids, guidance=None,
                         condition_latents=None, condition_ids=None, model_config=None,
-                        lora: Optional[LoraSet] = None, c_t: float = 0.0):
+                        lora: Optional[LoraSet] = None, c_t: float = 0.0, scalar_dtype=None):
     """transformer.py:47-252 (tranformer_forward); with condition_latents=None it is also the
     stock diffusers FluxTransformer2DModel.forward that FluxPipeline.__call__ uses (entry A)."""
     model_config = model_config or {}
@@ -618,9 +618,13 @@ def transformer_forward(model: FluxTransformer2DModel, hidden_states, encoder_hi
     use_cond = condition_latents is not None
     x = lora.linear("x_embedder", model.x_embedder, hidden_states, ll)
     cond = lora.linear("x_embedder", model.x_embedder, condition_latents, True) if use_cond else None
-    timestep = timestep.to(x.dtype) * 1000
+    # `scalar_dtype`: dtype in which the reference scales timestep / guidance by 1000
+    # (transformer.py:95,98 — the model dtype, i.e. bf16: 3.5 -> 3504).  An fp32 "true value" run
+    # passes torch.bfloat16 here so that it evaluates the SAME function of the inputs.
+    sd = scalar_dtype or x.dtype
+    timestep = (timestep.to(sd) * 1000).to(x.dtype)
     if guidance is not None:
-        guidance = guidance.to(x.dtype) * 1000
+        guidance = (guidance.to(sd) * 1000).to(x.dtype)
         temb = model.time_text_embed(timestep, guidance, pooled_projections)
         cond_temb = model.time_text_embed(torch.ones_like(timestep) * c_t * 1000,
                                           torch.ones_like(guidance) * 1000, pooled_projections)
@@ -726,20 +730,22 @@ def get_noises(max_seed: int, num_samples: int, height: int, width: int, dtype=t
 @torch.no_grad()
 def denoise(model, latents, prompt_embeds, pooled, num_inference_steps: int, guidance_scale=3.5,
             img_ids=None, txt_ids=None, condition_latents=None, cond_ids=None, model_config=None,
-            lora=None, return_trajectory=False):
+            lora=None, return_trajectory=False, scalar_dtype=None):
     """generate.py:193-276 (== FluxPipeline.__call__ steps 5-6 when condition_latents is None)."""
     dtype = latents.dtype
     timesteps, sigmas = flow_match_sigmas(num_inference_steps, latents.shape[1])
     if txt_ids is None:
         txt_ids = torch.zeros(prompt_embeds.shape[1], 3, dtype=dtype)
     traj = []
+    sd = scalar_dtype or dtype
     for i, t in enumerate(timesteps):
-        timestep = t.expand(latents.shape[0]).to(dtype)
+        timestep = t.expand(latents.shape[0]).to(sd)  # generate.py:222 rounds t to the model dtype
         guidance = None
         if model.config.guidance_embeds:
             guidance = torch.tensor([guidance_scale]).expand(latents.shape[0])
         v = transformer_forward(model, latents, prompt_embeds, pooled, timestep / 1000, img_ids,
-                                txt_ids, guidance, condition_latents, cond_ids, model_config, lora)
+                                txt_ids, guidance, condition_latents, cond_ids, model_config, lora,
+                                scalar_dtype=sd)
         latents = euler_step(latents, v, sigmas[i], sigmas[i + 1])
         if return_trajectory:
             traj.append((v, latents))

@@ -275,6 +275,16 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
   }
 }
 
+int attention_init() {
+  static bool attr_set = false;
+  if (!attr_set) {
+    RF_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kAttnSmem));
+    attr_set = true;
+  }
+  return 0;
+}
+
 int attention_launch(const AttnArgs& a, cudaStream_t stream) {
   if (a.n_tok <= 0 || a.heads <= 0 || a.batch <= 0) {
     set_error("attention_launch: empty problem");
@@ -310,12 +320,7 @@ int attention_launch(const AttnArgs& a, cudaStream_t stream) {
   const float kLog2e = 1.4426950408889634f;
   p.scale_log2 = kLog2e * 0.08838834764831845f;  // 1/sqrt(128)
   p.bias_log2 = kLog2e * a.cond_bias;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RF_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kAttnSmem));
-    attr_set = true;
-  }
+  if (int rc = attention_init()) return rc;
   const int grid = p.q_tiles * a.heads * a.batch;
   attn_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(p);
   RF_CHECK_CUDA(cudaGetLastError());

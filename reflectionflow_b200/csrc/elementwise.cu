@@ -165,15 +165,24 @@ gemv_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ W,
 }
 
 template <int NB>
-static int gemv_launch_nb(const bf16* x, int ldx, const bf16* W, const bf16* bias, bf16* y,
-                          int ldy, int N, int K, int act, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(NB) * K * sizeof(float);
+static int gemv_set_attr() {
   static bool attr_set = false;
   if (!attr_set) {
     RF_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       8 * 4096 * 4));
+                                       NB * 4096 * 4));
     attr_set = true;
   }
+  return 0;
+}
+int gemv_init() {
+  return (gemv_set_attr<1>() | gemv_set_attr<2>() | gemv_set_attr<4>() | gemv_set_attr<8>()) ? -2 : 0;
+}
+
+template <int NB>
+static int gemv_launch_nb(const bf16* x, int ldx, const bf16* W, const bf16* bias, bf16* y,
+                          int ldy, int N, int K, int act, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(NB) * K * sizeof(float);
+  if (int rc = gemv_set_attr<NB>()) return rc;
   int blocks = (N + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   gemv_kernel<NB><<<blocks, 256, smem, stream>>>(x, ldx, W, bias, y, ldy, N, K, act);

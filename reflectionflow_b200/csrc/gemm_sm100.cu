@@ -398,15 +398,31 @@ static int num_sms() {
 }
 
 template <int BN, int EPI>
-static int launch_cfg(const GemmParamsDev& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+static int set_attr() {
   static bool attr_set = false;
   if (!attr_set) {
     RF_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
+                                       GemmCfg<BN>::kSmemBytes));
     attr_set = true;
   }
+  return 0;
+}
+
+int gemm_init() {
+  int rc = 0;
+  rc |= set_attr<256, EPI_BIAS>(); rc |= set_attr<256, EPI_GELU>();
+  rc |= set_attr<256, EPI_GATE_RES>(); rc |= set_attr<256, EPI_QKV>();
+  rc |= set_attr<128, EPI_BIAS>(); rc |= set_attr<128, EPI_GELU>();
+  rc |= set_attr<128, EPI_GATE_RES>(); rc |= set_attr<128, EPI_QKV>();
+  rc |= set_attr<64, EPI_BIAS>(); rc |= set_attr<64, EPI_GELU>(); rc |= set_attr<64, EPI_GATE_RES>();
+  return rc ? -2 : 0;
+}
+
+template <int BN, int EPI>
+static int launch_cfg(const GemmParamsDev& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  if (int rc = set_attr<BN, EPI>()) return rc;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   gemm_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   RF_CHECK_CUDA(cudaGetLastError());
