@@ -148,6 +148,13 @@ int rf_dit_denoise(rf_dit* h, void* latents_inout, const void* txt, const void* 
                    const uint16_t* timesteps_bf16_host, const float* sigmas_host, int n_steps,
                    float guidance_scale, const void* cond_latents, void* stream);
 
+/* Per-kernel timing of everything launched between start and stop (CUDA events on the launching
+ * stream around each launch; graph-captured launches are skipped).  rf_profile_stop synchronises
+ * the device and writes a JSON object {kernel: {launches, ms, flops, bytes}} (algorithmic FLOPs /
+ * HBM bytes as documented in DESIGN.md) into json_out. */
+int rf_profile_start(void);
+int rf_profile_stop(char* json_out, int capacity);
+
 /* number of kernels this library launched since process start (for bench.py's gpu_launches) */
 int64_t rf_launch_count(void);
 

@@ -26,6 +26,9 @@ def _declare(lib):
     lib.rf_last_error.argtypes = []
     lib.rf_abi_version.restype = ci
     lib.rf_launch_count.restype = c_int64
+    lib.rf_profile_start.restype = ci
+    lib.rf_profile_stop.restype = ci
+    lib.rf_profile_stop.argtypes = [c_char_p, ci]
     lib.rf_op_linear.restype = ci
     lib.rf_op_linear.argtypes = [ci, ci, ci, ci, vp, ci, vp, vp, vp, ci, vp, ci, vp, ci, vp, vp, vp,
                                  vp, vp, vp]
@@ -76,6 +79,17 @@ def check(rc: int, what: str = "rf call"):
     if rc != 0:
         msg = load().rf_last_error()
         raise RFError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def profile_start():
+    check(load().rf_profile_start(), "rf_profile_start")
+
+
+def profile_stop() -> dict:
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(load().rf_profile_stop(buf, len(buf)), "rf_profile_stop")
+    return json.loads(buf.value.decode())
 
 
 def ptr(t):

@@ -322,6 +322,10 @@ int attention_launch(const AttnArgs& a, cudaStream_t stream) {
   p.bias_log2 = kLog2e * a.cond_bias;
   if (int rc = attention_init()) return rc;
   const int grid = p.q_tiles * a.heads * a.batch;
+  // algorithmic FLOPs: QK^T and PV only (4 * n^2 * 128 per head); bytes: q,k,v read + o written
+  const double n = a.n_tok;
+  ProfScope prof("attention", 4.0 * n * n * 128.0 * a.heads * a.batch,
+                 2.0 * 4.0 * n * 128.0 * a.heads * a.batch, stream);
   attn_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(p);
   RF_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -100,6 +100,7 @@ int ln_modulate_launch(const bf16* x, int ldx, bf16* out, int ldo, int rows, int
   if (rows <= 0) return 0;
   const int warps_per_block = 8;
   const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  ProfScope prof("ln_modulate", 0.0, 4.0 * rows * dim, stream);
   ln_modulate_kernel<<<blocks, 256, 0, stream>>>(x, ldx, out, ldo, rows, dim, scale, shift,
                                                  rows_per_batch > 0 ? rows_per_batch : rows,
                                                  mod_stride);
@@ -185,6 +186,7 @@ static int gemv_launch_nb(const bf16* x, int ldx, const bf16* W, const bf16* bia
   if (int rc = gemv_set_attr<NB>()) return rc;
   int blocks = (N + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope prof("gemv", 2.0 * NB * N * K, 2.0 * N * K, stream);
   gemv_kernel<NB><<<blocks, 256, smem, stream>>>(x, ldx, W, bias, y, ldy, N, K, act);
   RF_CHECK_CUDA(cudaGetLastError());
   count_launch();

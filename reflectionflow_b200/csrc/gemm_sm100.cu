@@ -424,6 +424,12 @@ static int launch_cfg(const GemmParamsDev& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   if (int rc = set_attr<BN, EPI>()) return rc;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  double rows = 0;
+  for (int g = 0; g < p.ngroups; ++g) rows += p.g[g].M;
+  static const char* kNames[4] = {"gemm_bias", "gemm_gelu", "gemm_gate_res", "gemm_qkv_rms_rope"};
+  // algorithmic FLOPs: 2 M N K; algorithmic bytes: A + W + out once
+  ProfScope prof(kNames[EPI], 2.0 * rows * p.N * p.K,
+                 2.0 * (rows * p.K + static_cast<double>(p.ngroups) * p.N * p.K + rows * p.N), stream);
   gemm_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
   RF_CHECK_CUDA(cudaGetLastError());
   count_launch();

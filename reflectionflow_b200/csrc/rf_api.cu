@@ -1,6 +1,8 @@
 // rf_api.cu — operator-level C ABI (include/rf_b200.h) over the kernel launchers.
 #include <atomic>
 #include <cstring>
+#include <map>
+#include <vector>
 
 #include "../../include/rf_b200.h"
 #include "rf_internal.h"
@@ -12,6 +14,28 @@ const char* get_error() { return g_err.c_str(); }
 static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+struct ProfRec {
+  const char* name;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+ProfScope::ProfScope(const char* name, double flops, double bytes, cudaStream_t s)
+    : idx(-1), stream(s) {
+  if (!g_prof_on) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+  ProfRec r{name, flops, bytes, nullptr, nullptr};
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, s);
+  g_prof.push_back(r);
+  idx = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(g_prof[idx].e1, stream);
+}
 }  // namespace rf
 
 using rf::bf16;
@@ -21,6 +45,52 @@ extern "C" {
 const char* rf_last_error(void) { return rf::get_error(); }
 int rf_abi_version(void) { return RF_B200_ABI_VERSION; }
 int64_t rf_launch_count(void) { return rf::launch_count(); }
+
+int rf_profile_start(void) {
+  for (auto& r : rf::g_prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  rf::g_prof.clear();
+  rf::g_prof_on = true;
+  return 0;
+}
+
+int rf_profile_stop(char* json_out, int capacity) {
+  rf::g_prof_on = false;
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    rf::set_error("rf_profile_stop: device synchronize failed");
+    return -2;
+  }
+  struct Agg { int n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : rf::g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    Agg& a = agg[r.name];
+    a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  rf::g_prof.clear();
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"launches\": %d, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+             first ? "" : ", ", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops,
+             kv.second.bytes);
+    js += buf;
+    first = false;
+  }
+  js += "}";
+  if (!json_out || capacity <= static_cast<int>(js.size())) {
+    rf::set_error("rf_profile_stop: buffer too small");
+    return -1;
+  }
+  memcpy(json_out, js.c_str(), js.size() + 1);
+  return 0;
+}
 
 int rf_op_linear(int epilogue, int M, int N, int K, const void* x, int ldx, const void* W,
                  const void* bias, void* y, int ldy, const void* addend, int ld_addend,

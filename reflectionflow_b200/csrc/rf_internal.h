@@ -28,6 +28,15 @@ int64_t launch_count();
     }                                                                                    \
   } while (0)
 
+// Optional per-launch timing (rf_profile_start/stop): CUDA events around every kernel launch on
+// the launching stream, aggregated per kernel name with its algorithmic FLOPs / bytes.
+struct ProfScope {
+  ProfScope(const char* name, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+  int idx;
+  cudaStream_t stream;
+};
+
 // Encode a 2-D bf16 row-major tensor map with 128-byte swizzle.
 //   rows x cols elements, row pitch ld (elements); box = box_rows x 64 columns.
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
