@@ -1,0 +1,395 @@
+"""ReflectionFlow search loop on B200s — mirror of tts/tts_reflectionflow.py (sample :94-463,
+main :466-629): per round  score parents -> top-k -> reflect -> refine prompt -> regenerate each
+candidate conditioned on its parent -> re-score -> chain bookkeeping.
+
+What changes, and why:
+  * candidates of a round are sharded over the ranks (candidate i -> rank i mod world); each rank
+    runs full denoise trajectories on its own GPU; ONE all-gather of score records (+ one of the
+    candidates' packed latents, the next round's parents) per round; every rank then runs the same
+    deterministic selection, so all ranks agree on top-k indices bit for bit;
+  * the boundary is explicit: init noise = the `noises` the caller sampled (the reference samples
+    them but never passes them on, App. B.1), condition latents are given tensors (the reference
+    samples the VAE posterior, B.4);
+  * images cross rounds as latents in HBM, not PNG files re-opened from disk; PNGs are written only
+    when a VAE is attached.  Until VAE decode/encode are native, the 512x512 condition of a parent
+    is formed in latent space (2x2 average pool of the parent's 128x128 latent grid) — a labelled
+    stand-in for decode -> resize -> encode.
+Artefact layout and names (midimg/<round>_round@<seed>.png, best_img_meta.jsonl,
+best_img_detailedscore.jsonl, samples_best/, samples_lastround/, samples_path_bestround/) follow the
+reference so downstream tools keep working."""
+from __future__ import annotations
+
+import copy
+import json
+import os
+import time
+from typing import Callable, Dict, List, Optional, Union
+
+import torch
+
+from ..pipeline import Condition, generate as _generate
+from . import search as S
+from .dist import DistCtx
+from .utils import TORCH_DTYPE_MAP, get_latent_prep_fn, get_noises, parse_cli_args
+from .verifiers import Candidate, HashTextEncoder, StubReflector, StubVerifier, load_verifier
+
+MAX_SEED = S.MAX_SEED
+MAX_RETRIES = 5
+RETRY_DELAY = 2
+
+
+def parent_condition_latents(parent_latents: torch.Tensor, height: int, width: int,
+                             condition_size: int) -> torch.Tensor:
+    """[1, (h/16)(w/16), 64] final latent of the parent -> packed [1, (c/16)^2, 64] condition tokens.
+    Stand-in for `vae.decode -> resize(condition_size) -> vae.encode` (tts_reflectionflow.py:273-279,
+    pipeline_tools.py:7-30) until the VAE is native: area-average the latent grid."""
+    b, n, c = parent_latents.shape
+    h, w = 2 * (height // 16), 2 * (width // 16)
+    x = parent_latents.float().view(b, h // 2, w // 2, c // 4, 2, 2).permute(0, 3, 1, 4, 2, 5)
+    x = x.reshape(b, c // 4, h, w)
+    ch = cw = condition_size // 8
+    x = torch.nn.functional.adaptive_avg_pool2d(x, (ch, cw))
+    x = x.view(b, c // 4, ch // 2, 2, cw // 2, 2).permute(0, 2, 4, 1, 3, 5)
+    return x.reshape(b, (ch // 2) * (cw // 2), c).to(parent_latents.dtype)
+
+
+def _save_candidate(cand: Candidate, path: str):
+    if cand.image is not None:
+        cand.image.save(path)
+    else:
+        torch.save(cand.latents.cpu(), os.path.splitext(path)[0] + ".latent.pt")
+
+
+def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
+           updated_prompt: Union[str, List[str]], reflections: Union[str, List[str]],
+           search_round: int, pipe, topk: int, root_dir: str, config: dict,
+           sample_path_lastround: str, sample_path_best: str, sample_path_bestround: str,
+           imagetoupdate: List[Candidate], midimg_path: str, total_rounds: int, chains: dict,
+           tag: Optional[str] = None, *, verifier=None, reflector=None, ctx: Optional[DistCtx] = None,
+           generate_fn: Callable = _generate) -> dict:
+    ctx = ctx or DistCtx()
+    verifier = verifier or StubVerifier(config["verifier_args"].get("name", "openai"))
+    reflector = reflector or StubReflector()
+    flag_terminated = search_round == total_rounds
+    config_cp = copy.deepcopy(config)
+    verifier_name = config["verifier_args"].get("name", "openai")
+    refine_args = config["refine_args"]
+    choice_of_metric = refine_args.get("choice_of_metric", None)
+    reflection_args = config_cp.get("reflection_args", None)
+    num_samples = len(noises)
+    rank0 = ctx.rank == 0
+    pa = config_cp["pipeline_args"]
+
+    # ---- 1. score the parents (sharded) and exchange the records
+    t0 = time.time()
+    n_prev = len(imagetoupdate)
+    mine = ctx.my_candidates(n_prev)
+    local_out = verifier.score([imagetoupdate[i] for i in mine], [original_prompt] * len(mine))
+    outputs = _exchange_outputs(ctx, verifier_name, choice_of_metric, imagetoupdate, mine, local_out)
+    sorted_list = S.sort_outputs(outputs, verifier_name, choice_of_metric)
+    if rank0:
+        print(f"Time taken for evaluation: {time.time() - t0} seconds")
+
+    # ---- 2. top-k (identical on every rank)
+    topk_idx, selected, selected_outputs = S.select_topk(outputs, sorted_list, imagetoupdate, topk)
+    selected_imgs = [c.name for c in selected]
+    if rank0:
+        with open(os.path.join(root_dir, "best_img_detailedscore.jsonl"), "a") as f:
+            f.write(json.dumps({"evaluation": selected_outputs, "filenames_batch": selected_imgs}) + "\n")
+
+    # ---- 3./4. reflections and prompt refinement: rank 0 asks the LLM hooks, everybody gets the text
+    reflection_performed = refinement_performed = False
+    update_reflections, refined_prompt = None, None
+    evaluations = [json.dumps(o) for o in selected_outputs]
+    if reflection_args and reflection_args.get("run_reflection", False):
+        t0 = time.time()
+        if rank0:
+            retries = 0
+            while True:
+                try:
+                    update_reflections = reflector.generate_reflections(
+                        selected, original_prompt, updated_prompt, reflections, evaluations)
+                    break
+                except Exception as e:  # tts_reflectionflow.py:208-219
+                    retries += 1
+                    if retries >= MAX_RETRIES:
+                        raise
+                    print(f"Error generating reflection: {e}. Retrying in {RETRY_DELAY} seconds...")
+                    time.sleep(RETRY_DELAY)
+        update_reflections = ctx.broadcast_object(update_reflections)
+        reflection_performed = True
+        if rank0:
+            print(f"Time taken for reflection generation: {time.time() - t0} seconds")
+    prompt_refiner_args = config_cp.get("prompt_refiner_args", None)
+    if prompt_refiner_args and prompt_refiner_args.get("run_refinement", False):
+        t0 = time.time()
+        if rank0:
+            refined_prompt = reflector.refine_prompt(
+                selected, original_prompt, updated_prompt, update_reflections,
+                evaluations if verifier_name == "openai" else None)
+        refined_prompt = ctx.broadcast_object(refined_prompt)
+        refinement_performed = True
+        if rank0:
+            print(f"Time taken for prompt refinement: {time.time() - t0} seconds")
+    if rank0 and (reflection_performed or refinement_performed):
+        with open(os.path.join(root_dir, "best_img_meta.jsonl"), "a") as f:
+            if reflection_performed:
+                f.write(f"reflections{search_round}: " + json.dumps(update_reflections) + "\n")
+            if refinement_performed:
+                f.write(f"refined_prompt{search_round}: " + json.dumps(refined_prompt) + "\n")
+            f.write(f"filenames_batch{search_round}: " + json.dumps(selected_imgs) + "\n")
+
+    # ---- 5./6. prompts and conditions (tts_reflectionflow.py:273-294)
+    if reflection_args and reflection_args.get("run_reflection", False):
+        base = refined_prompt if refined_prompt is not None else updated_prompt
+        prompts = S.compose_prompts(base, update_reflections)
+    else:
+        prompts = [original_prompt] * num_samples
+    cond_size = pa["condition_size"]
+    position_delta = [0, -cond_size // 16]
+
+    # ---- 7. regenerate: my share of the candidates, one full trajectory each
+    t0 = time.time()
+    noise_items = list(noises.items())
+    full_imgnames = [os.path.join(midimg_path, f"{search_round}_round@{seed}.png") for seed, _ in noise_items]
+    new_local = []
+    for i in ctx.my_candidates(num_samples):
+        seed, noise = noise_items[i]
+        parent = selected[i]
+        cond_lat = parent_condition_latents(parent.latents, pa["height"], pa["width"], cond_size)
+        cond = Condition("cot", latents=cond_lat, position_delta=position_delta)
+        result = generate_fn(pipe, prompt=[prompts[i]], conditions=[cond], height=pa["height"],
+                             width=pa["width"], model_config=config.get("model", None),
+                             default_lora=True, latents=noise,
+                             output_type="latent" if getattr(pipe, "vae", None) is None else "pil")
+        lat = result.images if getattr(pipe, "vae", None) is None else None
+        img = None if lat is not None else result.images[0]
+        new_local.append((i, Candidate(full_imgnames[i], seed, latents=lat, image=img)))
+    if rank0:
+        print(f"Time taken for image generation: {time.time() - t0} seconds")
+
+    # ---- 8. exchange: latents of all new candidates (next round's parents), then their scores
+    shape = tuple(new_local[0][1].latents.shape) if new_local else tuple(noise_items[0][1].shape)
+    shape = tuple(ctx.broadcast_object(shape))
+    all_lat = ctx.gather_latents([(i, c.latents) for i, c in new_local], num_samples, shape,
+                                 torch.bfloat16)
+    new_cands = [Candidate(full_imgnames[i], noise_items[i][0], latents=all_lat[i])
+                 for i in range(num_samples)]
+    for i, c in new_local:
+        new_cands[i].image = c.image
+        _save_candidate(new_cands[i], full_imgnames[i])
+    t0 = time.time()
+    mine = ctx.my_candidates(num_samples)
+    local_out = verifier.score([new_cands[i] for i in mine], [original_prompt] * len(mine))
+    outputs = _exchange_outputs(ctx, verifier_name, choice_of_metric, new_cands, mine, local_out)
+    if rank0:
+        print(f"Time taken for evaluation: {time.time() - t0} seconds")
+
+    # ---- 9. chains / best-of bookkeeping (identical on every rank; files from rank 0)
+    S.update_chains(chains, search_round, full_imgnames, outputs, selected_imgs, verifier_name,
+                    choice_of_metric)
+    by_name = {c.name: c for c in list(imagetoupdate) + new_cands}
+    if rank0:
+        if search_round == total_rounds:
+            for i, c in enumerate(new_cands):
+                _save_candidate(c, os.path.join(sample_path_lastround, f"{i:05}.png"))
+        if search_round == 1:
+            for i, c in enumerate(new_cands):
+                _save_candidate(c, os.path.join(sample_path_bestround, f"{i:05}.png"))
+        else:
+            for i, name in enumerate(S.best_per_chain(chains, verifier_name)):
+                if name in by_name:
+                    _save_candidate(by_name[name], os.path.join(sample_path_bestround, f"{i:05}.png"))
+        if search_round == total_rounds:
+            best = S.global_best(chains, verifier_name)
+            if best in by_name:
+                # the reference names this file with a leaked loop index (App. B.9); we use 00000
+                _save_candidate(by_name[best], os.path.join(sample_path_best, f"{0:05}.png"))
+
+    datapoint = {"original_prompt": original_prompt, "search_round": search_round,
+                 "num_noises": len(noises), "choice_of_metric": choice_of_metric,
+                 "generated_img": full_imgnames, "generated": new_cands,
+                 "flag_terminated": flag_terminated, "chains": chains, "topk_idx": topk_idx,
+                 "scores": outputs}
+    if refinement_performed:
+        datapoint["refined_prompt"] = refined_prompt
+    if reflection_performed:
+        datapoint["reflections"] = update_reflections
+    return datapoint
+
+
+def _exchange_outputs(ctx: DistCtx, verifier_name: str, metric: str, cands: List[Candidate],
+                      mine: List[int], local_out: List[dict]) -> List[dict]:
+    """All-gather fixed-size (cand_id, seed, label, score) records and rebuild the reference-shaped
+    output dicts in candidate order on every rank."""
+    recs = []
+    for i, o in zip(mine, local_out):
+        if verifier_name == "nvila":
+            recs.append((i, cands[i].seed, 1 if o["label"] == "yes" else 0, float(o["score"])))
+        else:
+            recs.append((i, cands[i].seed, 1, float(S.metric_value(o, metric))))
+    allr = ctx.gather_records(recs, len(cands))
+    outs = []
+    for cid, seed, label, score in allr:
+        if verifier_name == "nvila":
+            outs.append({"image_name": cands[cid].name, "label": "yes" if label else "no", "score": score})
+        else:
+            sc = int(score) if float(score).is_integer() else score
+            outs.append({metric: {"score": sc, "explanation": ""}, "image_name": cands[cid].name})
+    return outs
+
+
+def build_pipeline(config: dict, args, ctx: DistCtx):
+    """DiffusionPipeline.from_pretrained(...).to("cuda") + load_lora_weights
+    (tts_reflectionflow.py:498-505).  Offline (--synthetic): random-init weights of the FLUX.1-dev
+    architecture, seeded identically on every rank, random LoRA, hash text embeddings."""
+    from ..config import FluxDiTConfig
+    from ..pipeline import B200FluxPipeline
+    pa = config["pipeline_args"]
+    cfg = FluxDiTConfig()
+    if getattr(args, "layers", None):
+        nl, ns = (int(v) for v in args.layers.split(","))
+        cfg = FluxDiTConfig(num_layers=nl, num_single_layers=ns)
+    lora_path = pa.get("lora_path", None)
+    if not getattr(args, "synthetic", False):
+        raise RuntimeError("no FLUX.1-dev checkpoint is reachable offline: run with --synthetic, or "
+                           "build B200FluxPipeline.from_state_dict(...) yourself and call sample()")
+    pipe = B200FluxPipeline.from_synthetic(cfg, seed=0, device=ctx.device,
+                                           lora_rank=32 if lora_path is not None else 0)
+    pipe.text_encoder_hook = HashTextEncoder(cfg.joint_attention_dim, cfg.pooled_projection_dim)
+    if lora_path is not None:
+        pipe.load_lora_weights(synthetic_lora(cfg, seed=1), adapter_name="reflection")
+    pipe.set_progress_bar_config(disable=True)
+    return pipe
+
+
+def synthetic_lora(cfg, rank: int = 32, seed: int = 1):
+    """Random LoRA factors on the target list of train_flux/config.yaml:53."""
+    d = cfg.inner_dim
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+
+    def add(name, o, i):
+        out[name] = ((torch.randn(rank, i, generator=g) / i ** 0.5).to(torch.bfloat16),
+                     (torch.randn(o, rank, generator=g) * (0.5 / rank ** 0.5)).to(torch.bfloat16))
+    add("x_embedder", d, cfg.in_channels)
+    for i in range(cfg.num_layers):
+        p = f"transformer_blocks.{i}."
+        add(p + "norm1.linear", 6 * d, d)
+        for n in ("attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0"):
+            add(p + n, d, d)
+        add(p + "ff.net.2", d, 4 * d)
+    for i in range(cfg.num_single_layers):
+        p = f"single_transformer_blocks.{i}."
+        add(p + "norm.linear", 3 * d, d)
+        add(p + "proj_mlp", 4 * d, d)
+        add(p + "proj_out", d, 5 * d)
+        for n in ("attn.to_q", "attn.to_k", "attn.to_v"):
+            add(p + n, d, d)
+    return out
+
+
+@torch.no_grad()
+def main(argv=None, ctx: Optional[DistCtx] = None):
+    """tts_reflectionflow.py:466-629.  `--imgpath` holds the round-0 candidates written by the
+    noise-scaling stage (NNNNN/{metadata.jsonl, samples/*}); each rank owns a share of every round."""
+    args = parse_cli_args(argv)
+    with open(args.pipeline_config_path, "r") as f:
+        config = json.load(f)
+    config.update(vars(args))
+    ctx = ctx or DistCtx.from_env()
+    if args.seed is not None:
+        torch.manual_seed(args.seed)
+    else:  # the reference is unseeded; ranks must still agree on the seed stream
+        torch.manual_seed(int(ctx.broadcast_object(int(torch.seed() % (2 ** 31)))))
+    search_rounds = config["search_args"]["search_rounds"]
+    search_branch = config["search_args"]["search_branch"]
+    pipeline_name = config["pipeline_args"].get("pretrained_model_name_or_path")
+    root_dir = config["output_dir"]
+    os.makedirs(root_dir, exist_ok=True)
+    torch_dtype = TORCH_DTYPE_MAP[config["pipeline_args"].get("torch_dtype")]
+    pipe = build_pipeline(config, args, ctx)
+    verifier_args = config["verifier_args"]
+    verifier_name = verifier_args.get("name", "openai")
+    verifier = load_verifier(verifier_args, args.synthetic,
+                             config["refine_args"].get("choice_of_metric", "overall_score"))
+    reflector = StubReflector()
+    use_reflection = (config.get("reflection_args") or {}).get("run_reflection", False)
+    use_refine = (config.get("prompt_refiner_args") or {}).get("run_refinement", False)
+
+    metadatas = []
+    for folder_name in sorted(os.listdir(args.imgpath)):
+        folder_path = os.path.join(args.imgpath, folder_name)
+        if not os.path.isdir(folder_path):
+            continue
+        with open(os.path.join(folder_path, "metadata.jsonl"), "r") as f:
+            metadata = [json.loads(line) for line in f]
+        samples_path = os.path.join(folder_path, "samples")
+        images = []
+        if os.path.exists(samples_path):
+            images = [os.path.join(samples_path, fn) for fn in sorted(os.listdir(samples_path))]
+        metadatas.append({"metadata": metadata, "images": images})
+    metadatas = metadatas[args.start_index:] if args.end_index == -1 else \
+        metadatas[args.start_index:args.end_index]
+
+    for index, metadata in enumerate(metadatas):
+        meta0 = metadata["metadata"][0]
+        outpath = os.path.join(root_dir, f"{index + args.start_index:0>5}")
+        dirs = {k: os.path.join(outpath, k) for k in
+                ("samples_lastround", "samples_best", "samples_path_bestround", "midimg")}
+        if ctx.rank == 0:
+            for d in dirs.values():
+                os.makedirs(d, exist_ok=True)
+            with open(os.path.join(outpath, "metadata.jsonl"), "w") as fp:
+                json.dump(meta0, fp)
+        ctx.barrier()
+        updated_prompt = [meta0["prompt"]] * search_branch
+        original_prompt = meta0["prompt"]
+        reflections = [""] * search_branch if use_reflection else None
+        imagetoupdate = load_round0(metadata["images"], ctx)
+        chains = {}
+        for rnd in range(1, search_rounds + 1):
+            if ctx.rank == 0:
+                print(f"\n=== Round: {rnd} ===")
+            noises = get_noises(max_seed=MAX_SEED, num_samples=search_branch,
+                                height=config["pipeline_args"]["height"],
+                                width=config["pipeline_args"]["width"], dtype=torch_dtype,
+                                fn=get_latent_prep_fn(pipeline_name))
+            dp = sample(noises=noises, original_prompt=original_prompt, updated_prompt=updated_prompt,
+                        reflections=reflections, search_round=rnd, pipe=pipe, topk=search_branch,
+                        root_dir=outpath, config=config,
+                        sample_path_lastround=dirs["samples_lastround"],
+                        sample_path_best=dirs["samples_best"],
+                        sample_path_bestround=dirs["samples_path_bestround"],
+                        imagetoupdate=imagetoupdate, midimg_path=dirs["midimg"],
+                        tag=meta0.get("tag"), total_rounds=search_rounds, chains=chains,
+                        verifier=verifier, reflector=reflector, ctx=ctx)
+            if use_reflection:
+                reflections = dp["reflections"]
+            if use_refine:
+                updated_prompt = dp["refined_prompt"]
+            imagetoupdate = dp["generated"]
+            chains = dp["chains"]
+            if dp["flag_terminated"]:
+                break
+    return 0
+
+
+def load_round0(paths: List[str], ctx: DistCtx) -> List[Candidate]:
+    """Round-0 candidates written by the noise-scaling stage: `<k>_round@<seed>.latent.pt` (or PNGs
+    once a VAE is attached — decoding them back needs the VAE encoder)."""
+    cands = []
+    for p in paths:
+        if not p.endswith(".latent.pt"):
+            continue
+        stem = os.path.basename(p)[: -len(".latent.pt")]
+        seed = int(stem.split("@")[-1]) if "@" in stem else 0
+        lat = torch.load(p, map_location="cpu").to(ctx.device)
+        cands.append(Candidate(os.path.splitext(p)[0][: -len(".latent")] + ".png", seed, latents=lat))
+    if not cands:
+        raise RuntimeError("no round-0 candidates (*.latent.pt) found under --imgpath")
+    return cands
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

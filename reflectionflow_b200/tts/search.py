@@ -50,7 +50,7 @@ def gather_records(local: Sequence[Tuple[int, int, int, float]], per_rank: int, 
     buf = bytearray()
     for i in range(per_rank):
         buf += pack_record(*local[i]) if i < len(local) else pack_record(-1, 0, 0, 0.0)
-    t = torch.frombuffer(bytes(buf), dtype=torch.uint8).clone().to(device)
+    t = torch.frombuffer(buf, dtype=torch.uint8).clone().to(device)
     if world > 1:
         out = torch.empty(world * t.numel(), dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(out, t)
@@ -64,3 +64,104 @@ def gather_records(local: Sequence[Tuple[int, int, int, float]], per_rank: int, 
 def gather_scores(score: torch.Tensor, rank: int, world: int, device):
     """bench helper: one record per rank."""
     return gather_records([(rank, 0, 1, float(score.reshape(-1)[0].item()))], 1, rank, world, device)
+
+
+# ------------------------------------------------------------------ selection rules (pinned by table tests)
+def metric_value(output: dict, choice_of_metric: str):
+    """tts_reflectionflow.py:152-155."""
+    v = output[choice_of_metric]
+    return v["score"] if isinstance(v, dict) else v
+
+
+def nvila_key(output: dict):
+    """tts_reflectionflow.py:165-169: "yes" first by descending score, then "no" by ascending."""
+    return (0, -output["score"]) if output["label"] == "yes" else (1, output["score"])
+
+
+def sort_outputs(outputs: List[dict], verifier_name: str, choice_of_metric: str = None) -> List[dict]:
+    if verifier_name == "openai":
+        return sorted(outputs, key=lambda x: metric_value(x, choice_of_metric), reverse=True)
+    if verifier_name == "nvila":
+        return sorted(outputs, key=nvila_key)
+    raise NotImplementedError(f"Verifier {verifier_name} not supported")
+
+
+def select_topk(outputs: List[dict], sorted_list: List[dict], items: list, topk: int):
+    """tts_reflectionflow.py:175-182.  `outputs.index(x)` returns the FIRST equal dict, so equal
+    score dicts collapse onto one index — kept on purpose."""
+    topk_scores = sorted_list[:topk]
+    topk_idx = [outputs.index(x) for x in topk_scores]
+    selected = [items[i] for i in topk_idx]
+    selected_outputs = [outputs[i] for i in topk_idx]
+    if topk > len(selected):
+        repeat = topk - len(selected)
+        selected = selected + selected[:repeat]
+        selected_outputs = selected_outputs + selected_outputs[:repeat]
+        topk_idx = topk_idx + topk_idx[:repeat]
+    return topk_idx, selected, selected_outputs
+
+
+def compose_prompts(refined_prompt: List[str], reflections: List[str]) -> List[str]:
+    """tts_reflectionflow.py:286-292."""
+    if reflections:
+        return [refined_prompt[i] + " [Reflexion]: " + reflections[i] for i in range(len(reflections))]
+    return list(refined_prompt)
+
+
+def update_chains(chains: Dict[str, dict], search_round: int, full_names: List[str],
+                  outputs: List[dict], selected_parents: List[str], verifier_name: str,
+                  choice_of_metric: str = None) -> Dict[str, dict]:
+    """tts_reflectionflow.py:359-396, including the asymmetry that the nvila branch stops at the
+    first chain containing the parent while the openai branch updates every such chain."""
+    if verifier_name not in ("openai", "nvila"):
+        raise NotImplementedError(f"Verifier {verifier_name} not supported")
+    if search_round == 1:
+        for i, name in enumerate(full_names):
+            if name not in chains:
+                chains[name] = {"images": [], "scores": []} if verifier_name == "openai" \
+                    else {"images": [], "scores": [], "labels": []}
+            chains[name]["images"].append(name)
+            if verifier_name == "openai":
+                chains[name]["scores"].append(outputs[i][choice_of_metric]["score"])
+            else:
+                chains[name]["labels"].append(outputs[i]["label"])
+                chains[name]["scores"].append(outputs[i]["score"])
+        return chains
+    for i, name in enumerate(full_names):
+        parent = selected_parents[i]
+        for key in chains:
+            if parent in chains[key]["images"]:
+                chains[key]["images"].append(name)
+                if verifier_name == "openai":
+                    chains[key]["scores"].append(outputs[i][choice_of_metric]["score"])
+                else:
+                    chains[key]["labels"].append(outputs[i]["label"])
+                    chains[key]["scores"].append(outputs[i]["score"])
+                    break
+    return chains
+
+
+def best_per_chain(chains: Dict[str, dict], verifier_name: str) -> List[str]:
+    """tts_reflectionflow.py:408-421."""
+    best = []
+    for chain in chains.values():
+        if verifier_name == "openai":
+            scores = chain["scores"]
+            idx = max(range(len(scores)), key=lambda j: (scores[j], -j))  # np.argmax: first max
+        else:
+            idx = min(range(len(chain["scores"])),
+                      key=lambda j: (0 if chain["labels"][j] == "yes" else 1,
+                                     -chain["scores"][j] if chain["labels"][j] == "yes"
+                                     else chain["scores"][j]))
+        best.append(chain["images"][idx])
+    return best
+
+
+def global_best(chains: Dict[str, dict], verifier_name: str) -> str:
+    """tts_reflectionflow.py:428-446."""
+    if verifier_name == "openai":
+        allv = [(s, n) for c in chains.values() for n, s in zip(c["images"], c["scores"])]
+        return sorted(allv, key=lambda x: x[0], reverse=True)[0][1]
+    allv = [(l, s, n) for c in chains.values()
+            for n, l, s in zip(c["images"], c["labels"], c["scores"])]
+    return sorted(allv, key=lambda x: (0 if x[0] == "yes" else 1, -x[1] if x[0] == "yes" else x[1]))[0][2]

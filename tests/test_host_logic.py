@@ -1,0 +1,150 @@
+"""not-gpu: host-side mirror of the reference interface — scheduler, noise factory, pipeline
+argument handling, config/CLI schema — checked against the oracle (no kernels involved)."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import flux_oracle as fo
+from reflectionflow_b200.pipeline import B200FluxPipeline, Condition, flow_match_schedule, generate
+from reflectionflow_b200.scheduler import FlowMatchEulerDiscreteScheduler, calculate_shift
+from reflectionflow_b200.tts import utils as U
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+class FakeTransformer:
+    """Records what the pipeline hands to the device loop (test-only; not a compute fallback)."""
+    device = torch.device("cpu")
+    config = _Cfg(in_channels=64, guidance_embeds=True)
+
+    def __init__(self):
+        self.calls = []
+
+    def denoise(self, latents, prompt_embeds, pooled, t_in, sigmas, guidance_scale, img_ids, txt_ids,
+                cond_latents=None, cond_ids=None, model_config=None, condition_scale=1.0):
+        self.calls.append(dict(latents=latents, t_in=t_in, sigmas=sigmas, g=guidance_scale,
+                               img_ids=img_ids, txt_ids=txt_ids, cond=cond_latents, cond_ids=cond_ids,
+                               mc=model_config, cs=condition_scale))
+        return latents
+
+
+@pytest.mark.parametrize("steps,seq", [(28, 4096), (4, 256), (50, 4096), (30, 1024)])
+def test_schedule_bit_identical_to_oracle(steps, seq):
+    ts, sig = flow_match_schedule(steps, seq)
+    ots, osig = fo.flow_match_sigmas(steps, seq)
+    assert torch.equal(ts, ots) and torch.equal(sig, osig)
+    assert calculate_shift(seq) == fo.calculate_shift(seq)
+
+
+def test_scheduler_object_surface():
+    s = FlowMatchEulerDiscreteScheduler()
+    assert s.order == 1 and s.config.base_image_seq_len == 256 and s.config.max_shift == 1.15
+    s.set_timesteps(sigmas=[1.0, 0.5], mu=0.5)
+    assert len(s.timesteps) == 2 and len(s.sigmas) == 3 and s.sigmas[-1] == 0
+
+
+def test_get_noises_matches_oracle_protocol():
+    torch.manual_seed(99)
+    a = U.get_noises(2 ** 31 - 1, 4, 256, 256)
+    torch.manual_seed(99)
+    b = fo.get_noises(2 ** 31 - 1, 4, 256, 256)
+    assert list(a) == list(b)
+    for k in a:
+        assert a[k].dtype == torch.bfloat16 and a[k].shape == (1, 256, 64) and torch.equal(a[k], b[k])
+    # side effect kept: the global RNG is left re-seeded with the last seed
+    nxt = torch.randint(0, 2 ** 31 - 1, (1,))
+    torch.manual_seed(list(a)[-1])
+    torch.randn((1, 16, 32, 32), dtype=torch.bfloat16)
+    assert torch.equal(nxt, torch.randint(0, 2 ** 31 - 1, (1,)))
+
+
+def test_pipeline_call_entry_a_hands_reference_timesteps_to_the_loop():
+    ft = FakeTransformer()
+    pipe = B200FluxPipeline(ft)
+    emb, pooled = torch.randn(2, 512, 4096), torch.randn(2, 768)
+    lat = torch.randn(2, 4096, 64).to(torch.bfloat16)
+    out = pipe(prompt_embeds=emb, pooled_prompt_embeds=pooled, latents=lat, guidance_scale=3.5,
+               num_inference_steps=28, height=1024, width=1024, output_type="latent")
+    assert out.images.shape == (2, 4096, 64)
+    c = ft.calls[0]
+    ts, sig = fo.flow_match_sigmas(28, 4096)
+    assert torch.equal(c["t_in"], ts.to(torch.bfloat16) / 1000) and torch.equal(c["sigmas"], sig)
+    assert c["img_ids"].shape == (4096, 3) and c["txt_ids"].shape == (512, 3) and c["cond"] is None
+    assert torch.equal(c["img_ids"].float(), fo.prepare_latent_image_ids(64, 64).float())
+
+
+def test_pipeline_errors_match_diffusers_semantics():
+    pipe = B200FluxPipeline(FakeTransformer())
+    e, p = torch.randn(1, 512, 4096), torch.randn(1, 768)
+    with pytest.raises(ValueError):
+        pipe(prompt_embeds=e, pooled_prompt_embeds=p, height=1000, width=1024, output_type="latent")
+    with pytest.raises(ValueError):
+        pipe(prompt="x", prompt_embeds=e, pooled_prompt_embeds=p, output_type="latent")
+    with pytest.raises(ValueError):
+        pipe(output_type="latent")
+    with pytest.raises(ValueError):
+        pipe(prompt_embeds=e, output_type="latent")
+    with pytest.raises(NotImplementedError):  # no text encoders attached
+        pipe(prompt="a cat", output_type="latent")
+    with pytest.raises(NotImplementedError):  # no VAE attached
+        pipe(prompt_embeds=e, pooled_prompt_embeds=p, height=64, width=64)
+
+
+def test_generate_entry_b_condition_ids_and_defaults():
+    ft = FakeTransformer()
+    pipe = B200FluxPipeline(ft)
+    e, p = torch.randn(1, 512, 4096), torch.randn(1, 768)
+    cond_lat = torch.randn(1, 1024, 64)
+    cond = Condition("cot", latents=cond_lat, position_delta=[0, -32])
+    out = generate(pipe, conditions=[cond], model_config={"union_cond_attn": True}, default_lora=True,
+                   prompt_embeds=e, pooled_prompt_embeds=p, height=1024, width=1024,
+                   output_type="latent")
+    c = ft.calls[0]
+    assert out.images.shape == (1, 4096, 64)
+    assert c["t_in"].numel() == 28 and c["g"] == 3.5  # defaults of generate.py:30,32
+    assert c["cond"].shape == (1, 1024, 64)
+    assert torch.equal(c["cond_ids"].float(), fo.condition_ids(512, (0, -32)).float())
+    with pytest.raises(AssertionError):
+        generate(pipe, conditions=[cond, cond], prompt_embeds=e, pooled_prompt_embeds=p,
+                 output_type="latent")
+    with pytest.raises(NotImplementedError):
+        Condition("depth", latents=cond_lat)
+    # defaults: 512 x 512 like generate.py:28-29
+    generate(pipe, conditions=None, prompt_embeds=e, pooled_prompt_embeds=p, output_type="latent")
+    assert ft.calls[-1]["latents"].shape == (1, 1024, 64) and ft.calls[-1]["cond"] is None
+
+
+def test_prepare_latents_cpu_generator_protocol():
+    pipe = B200FluxPipeline(FakeTransformer())
+    g = torch.Generator().manual_seed(5)
+    lat, ids = pipe.prepare_latents(1, 16, 256, 256, torch.bfloat16, "cpu", g)
+    g2 = torch.Generator().manual_seed(5)
+    ref = fo.pack_latents(torch.randn((1, 16, 32, 32), generator=g2, dtype=torch.bfloat16), 1, 16, 32, 32)
+    assert torch.equal(lat, ref) and ids.shape == (256, 3)
+
+
+def test_config_schema_and_cli():
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = json.load(open(os.path.join(here, "reflectionflow_b200", "tts", "configs",
+                                      "flux.1_dev_nvilascore.json")))
+    for sec in ("pipeline_args", "verifier_args", "refine_args", "search_args", "model",
+                "reflection_args", "prompt_refiner_args", "use_low_gpu_vram", "batch_size_for_img_gen"):
+        assert sec in cfg
+    assert set(cfg["model"]) == {"add_cond_attn", "latent_lora", "union_cond_attn"}
+    ref_cfg = "/root/reference/tts/configs/flux.1_dev_nvilascore.json"
+    if os.path.exists(ref_cfg):  # same schema as the reference's shipped config
+        r = json.load(open(ref_cfg))
+        assert set(r) == set(cfg)
+        for k in r:
+            if isinstance(r[k], dict):
+                assert set(r[k]) == set(cfg[k]), k
+    a = U.parse_cli_args(["--pipeline_config_path", "x.json", "--start_index", "3", "--imgpath", "d"])
+    assert a.pipeline_config_path == "x.json" and a.start_index == 3 and a.end_index == -1
+    assert a.output_dir == "output" and a.meta_path == "meta.jsonl" and a.imgpath == "d"
+    assert U.TORCH_DTYPE_MAP["bf16"] is torch.bfloat16
+    with pytest.raises(KeyError):
+        U.get_latent_prep_fn("stabilityai/stable-diffusion-xl-base-1.0")

@@ -1,0 +1,146 @@
+"""not-gpu: host logic of the sharded outer loop.  The denoiser is replaced by a cheap pure function
+(`fake_generate`, test-only) so that the round logic — sharding, the per-round all-gather of score
+records and parent latents, selection, chain bookkeeping, artefact layout — can run on CPU under
+gloo with world_size 2 and be compared with the single-process result."""
+import json
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from reflectionflow_b200.pipeline import FluxPipelineOutput  # noqa: E402
+from reflectionflow_b200.tts import reflectionflow as RF  # noqa: E402
+from reflectionflow_b200.tts import search as S  # noqa: E402
+from reflectionflow_b200.tts.dist import DistCtx  # noqa: E402
+from reflectionflow_b200.tts.utils import get_noises  # noqa: E402
+from reflectionflow_b200.tts.verifiers import Candidate, StubReflector, StubVerifier  # noqa: E402
+
+H = W = 64  # 16 image tokens
+CONFIG = {
+    "pipeline_args": {"pretrained_model_name_or_path": "black-forest-labs/FLUX.1-dev",
+                      "torch_dtype": "bf16", "height": H, "width": W, "condition_size": 32,
+                      "guidance_scale": 3.5, "num_inference_steps": 4, "lora_path": "x"},
+    "verifier_args": {"name": "nvila"},
+    "refine_args": {"choice_of_metric": "overall_score"},
+    "search_args": {"search_branch": 5, "search_rounds": 3},
+    "model": {"add_cond_attn": False, "latent_lora": False, "union_cond_attn": True},
+    "reflection_args": {"run_reflection": True, "name": "openai"},
+    "prompt_refiner_args": {"run_refinement": True},
+}
+
+
+class FakePipe:
+    vae = None
+
+
+def fake_generate(pipe, prompt=None, conditions=None, latents=None, **kw):
+    """test-only denoiser: deterministic function of (noise, parent condition, prompt)."""
+    cond = conditions[0].latents.float()
+    h = sum(ord(c) for c in prompt[0]) % 97 / 97.0
+    out = 0.5 * latents.float() + 0.25 * cond.mean() + 0.01 * h
+    out[..., : cond.shape[1] // 4, :] += 0.1 * cond[..., : cond.shape[1] // 4, :].mean()
+    return FluxPipelineOutput(images=out.to(torch.bfloat16))
+
+
+def run_rounds(ctx, tmp):
+    torch.manual_seed(1234)
+    rounds, branch = CONFIG["search_args"]["search_rounds"], CONFIG["search_args"]["search_branch"]
+    g = torch.Generator().manual_seed(7)
+    parents = [Candidate(f"r0/{i}.png", i, latents=torch.randn(1, 16, 64, generator=g).to(torch.bfloat16))
+               for i in range(branch)]
+    dirs = {k: os.path.join(tmp, k) for k in ("last", "best", "bestround", "mid")}
+    if ctx.rank == 0:
+        for d in dirs.values():
+            os.makedirs(d, exist_ok=True)
+    ctx.barrier()
+    chains, log = {}, []
+    upd, refl = ["a photo of a cat"] * branch, [""] * branch
+    for rnd in range(1, rounds + 1):
+        noises = get_noises(S.MAX_SEED, branch, H, W)
+        dp = RF.sample(noises, "a photo of a cat", upd, refl, rnd, FakePipe(), branch, tmp, CONFIG,
+                       dirs["last"], dirs["best"], dirs["bestround"], parents, dirs["mid"], rounds,
+                       chains, verifier=StubVerifier("nvila"), reflector=StubReflector(), ctx=ctx,
+                       generate_fn=fake_generate)
+        parents, chains = dp["generated"], dp["chains"]
+        upd, refl = dp["refined_prompt"], dp["reflections"]
+        log.append({"topk_idx": dp["topk_idx"], "seeds": [c.seed for c in parents],
+                    "scores": [(o["label"], o["score"]) for o in dp["scores"]],
+                    "lat_sum": [float(c.latents.float().sum()) for c in parents]})
+    return {"log": log, "chains": chains, "best": S.global_best(chains, "nvila")}
+
+
+def _worker(rank, world, port, base, q):
+    os.makedirs(base, exist_ok=True)
+    os.chdir(base)  # artefact names (which seed the stub hooks) must not depend on the temp dir
+    tmp = "run"
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = run_rounds(DistCtx(rank, world, "cpu"), tmp)
+    q.put((rank, json.dumps(res)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_single_process_rounds(tmp_path):
+    res = run_rounds(DistCtx(), str(tmp_path))
+    assert len(res["log"]) == 3
+    for r in res["log"]:
+        assert sorted(set(r["topk_idx"])) == sorted(set(r["topk_idx"])) and len(r["topk_idx"]) == 5
+    # artefacts follow the reference's layout
+    mid = sorted(os.listdir(tmp_path / "mid"))
+    assert len(mid) == 15 and all("_round@" in m for m in mid)
+    assert os.path.exists(tmp_path / "best_img_meta.jsonl")
+    lines = open(tmp_path / "best_img_detailedscore.jsonl").read().strip().splitlines()
+    assert len(lines) == 3 and "filenames_batch" in json.loads(lines[0])
+    assert len(os.listdir(tmp_path / "last")) == 5 and len(os.listdir(tmp_path / "best")) == 1
+    # chains: 5 roots, every later candidate attached to exactly one chain (nvila break rule)
+    assert len(res["chains"]) == 5
+    assert sum(len(c["images"]) for c in res["chains"].values()) == 15
+
+
+@pytest.mark.timeout(300)
+def test_world2_gloo_matches_single_process(tmp_path):
+    os.makedirs(tmp_path / "w1", exist_ok=True)
+    cwd = os.getcwd()
+    os.chdir(tmp_path / "w1")
+    try:
+        single = run_rounds(DistCtx(), "run")
+    finally:
+        os.chdir(cwd)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path / "w2"), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    r0, r1 = json.loads(got[0]), json.loads(got[1])
+    assert r0 == r1, "ranks disagree"
+    assert r0 == json.loads(json.dumps(single)), "sharded run differs from the single-process run"
+
+
+def test_parent_condition_latents_shape_and_mean():
+    lat = torch.randn(1, 4096, 64).to(torch.bfloat16)
+    c = RF.parent_condition_latents(lat, 1024, 1024, 512)
+    assert c.shape == (1, 1024, 64)
+    assert abs(c.float().mean().item() - lat.float().mean().item()) < 5e-3
