@@ -7,16 +7,12 @@
 // read by TMA straight out of the token-major [n_tok, heads*128] buffers the QKV GEMM epilogue
 // wrote, and O is written token-major so it is the A operand of the out-projection GEMM.
 //
-// One CTA = one 128-row query tile of one head; two CTAs are co-resident per SM so one CTA's
-// softmax overlaps the other's tensor-core work.
-//   warps 0..3  softmax / correction / epilogue: thread r owns score row r (tcgen05.ld 32x32b)
-//   warp 4      TMA producer (Q once, then K_j, V_j per 128-row KV tile)
-//   warp 5      MMA issuer: S = Q K_j^T (SS, both K-major), O += P V_j (A = P from TMEM,
-//               B = V MN-major from smem)
-// TMEM columns: [0,128) S (fp32), aliased by P (bf16, 64 columns) once a row has been read;
-//               [128,256) O (fp32).
-// Online softmax keeps a per-row running max that is only refreshed when it grows by more
-// than 2^8 (lazy rescale), so the O correction pass is rare.
+// One CTA = two 128-row query tiles of one head; two softmax warpgroups ping-pong so that the
+// tensor pipe works on one tile's QK^T / PV while the other tile's rows are in their softmax
+// (see the kernel comment).  K/V tiles stream through a 2-stage TMA ring.
+// Online softmax runs in the log2 domain and keeps a per-row reference max that is only
+// refreshed when it grows by more than 2^8 (lazy rescale), so the O correction pass is rare.
+// A masked (q tile, kv tile) pair of cond_mode 2 writes P = 0 and leaves the row statistics alone.
 #include <cuda.h>
 
 #include "rf_internal.h"
@@ -24,16 +20,17 @@
 
 namespace rf {
 
-static constexpr int kAttnThreads = 192;
+static constexpr int kAttnThreads = 320;  // 8 softmax warps (2 warpgroups) + TMA warp + MMA warp
 static constexpr int kTile = 128;
 static constexpr int kHalfBytes = kTile * 128;   // one [128 x 64] bf16 box = 16 KB
 static constexpr int kTileBytes = 2 * kHalfBytes;  // [128 x 128] bf16 = 32 KB
-static constexpr int kAttnSmem = 3 * kTileBytes + 1024 + 128;
+static constexpr int kKVStages = 2;
+static constexpr int kAttnSmem = (2 + 2 * kKVStages) * kTileBytes + 1024 + 256;
 
 struct alignas(64) AttnParamsDev {
   CUtensorMap tmQ, tmK, tmV;
   bf16* out;
-  int ldo, n_tok, heads, batch, q_tiles, kv_tiles;
+  int ldo, n_tok, heads, batch, q_pairs, kv_tiles;
   int n_main, cond_mode;
   float scale_log2;  // log2(e) / sqrt(128)
   float bias_log2;   // log2(e) * cond_bias
@@ -45,213 +42,257 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
+// One CTA = TWO 128-row query tiles of one head (FlashAttention-4 style ping-pong):
+//   warps 0..3  softmax warpgroup 0 (query tile 0), warps 4..7 softmax warpgroup 1 (tile 1);
+//               thread r of a warpgroup owns score row r (tcgen05.ld 32x32b: no shuffles)
+//   warp 8      TMA producer: Q0,Q1 once, then K_j / V_j through a 2-stage ring
+//   warp 9      MMA issuer, interleaved so the tensor pipe always has the OTHER tile's work while one
+//               warpgroup is in its softmax:   QK0_0 QK1_0 | PV0_j QK0_{j+1} PV1_j QK1_{j+1} | ...
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_t (bf16) aliases S_t.
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_kernel(const __grid_constant__ AttnParamsDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + kTileBytes;
-  uint8_t* sV = smem + 2 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kTileBytes);
+  uint8_t* sQ = smem;                                  // 2 tiles
+  uint8_t* sK = smem + 2 * kTileBytes;                 // kKVStages tiles
+  uint8_t* sV = sK + kKVStages * kTileBytes;           // kKVStages tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKVStages * kTileBytes);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = bars + 2;
-  uint64_t* v_full = bars + 3;
-  uint64_t* v_empty = bars + 4;
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2] per query tile
+  uint64_t* p_full = bars + 11;   // [2] per query tile
+  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // work decomposition: q tile fastest so that all q tiles of one head run together (K/V in L2)
+  // q pair fastest so that all CTAs of one head run together (its K/V stay in L2)
   int bid = blockIdx.x;
-  const int qt = bid % p.q_tiles;
-  bid /= p.q_tiles;
+  const int qp = bid % p.q_pairs;
+  bid /= p.q_pairs;
   const int head = bid % p.heads;
   const int b = bid / p.heads;
-  const int row_base = b * p.n_tok;  // first row of this batch element in the buffers
-  const int q0 = qt * kTile;
+  const int row_base = b * p.n_tok;
+  const int q0 = qp * 2 * kTile;
   const int col0 = head * 128;
-  const bool q_is_cond = (p.cond_mode != 0) && (q0 >= p.n_main);
+  const int n_kv = p.kv_tiles;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
   }
-  if (warp == 5 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     mbar_init(q_full, 1);
-    mbar_init(k_full, 1);
-    mbar_init(k_empty, 1);
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc<256>(tmem_slot);
+    tmem_alloc<512>(tmem_slot);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;        // S / P
-  const uint32_t tO = tmem_base + 128;  // O
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_2d(sQ, &p.tmQ, q_full, col0, row_base + q0);
-      tma_load_2d(sQ + kHalfBytes, &p.tmQ, q_full, col0 + 64, row_base + q0);
-      int it = 0;
-      for (int j = 0; j < p.kv_tiles; ++j) {
-        const bool cross = (p.cond_mode != 0) && ((j * kTile >= p.n_main) != q_is_cond);
-        if (p.cond_mode == 2 && cross) continue;
-        const uint32_t par = (it & 1) ^ 1;
-        mbar_wait(k_empty, par);
-        mbar_arrive_expect_tx(k_full, kTileBytes);
-        tma_load_2d(sK, &p.tmK, k_full, col0, row_base + j * kTile);
-        tma_load_2d(sK + kHalfBytes, &p.tmK, k_full, col0 + 64, row_base + j * kTile);
-        mbar_wait(v_empty, par);
-        mbar_arrive_expect_tx(v_full, kTileBytes);
-        tma_load_2d(sV, &p.tmV, v_full, col0, row_base + j * kTile);
-        tma_load_2d(sV + kHalfBytes, &p.tmV, v_full, col0 + 64, row_base + j * kTile);
-        ++it;
+      mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+      for (int t = 0; t < 2; ++t) {
+        tma_load_2d(sQ + t * kTileBytes, &p.tmQ, q_full, col0, row_base + q0 + t * kTile);
+        tma_load_2d(sQ + t * kTileBytes + kHalfBytes, &p.tmQ, q_full, col0 + 64,
+                    row_base + q0 + t * kTile);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t par = ((j >> 1) & 1) ^ 1;
+        uint8_t* kd = sK + st * kTileBytes;
+        uint8_t* vd = sV + st * kTileBytes;
+        mbar_wait(&k_empty[st], par);
+        mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+        tma_load_2d(kd, &p.tmK, &k_full[st], col0, row_base + j * kTile);
+        tma_load_2d(kd + kHalfBytes, &p.tmK, &k_full[st], col0 + 64, row_base + j * kTile);
+        mbar_wait(&v_empty[st], par);
+        mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+        tma_load_2d(vd, &p.tmV, &v_full[st], col0, row_base + j * kTile);
+        tma_load_2d(vd + kHalfBytes, &p.tmV, &v_full[st], col0 + 64, row_base + j * kTile);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);  // A, B K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (V) MN-major
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
-      mbar_wait(q_full, 0);
-      int it = 0;
-      for (int j = 0; j < p.kv_tiles; ++j) {
-        const bool cross = (p.cond_mode != 0) && ((j * kTile >= p.n_main) != q_is_cond);
-        if (p.cond_mode == 2 && cross) continue;
-        const uint32_t par = it & 1;
-        mbar_wait(k_full, par);
-        tc_fence_after();
+      auto issue_qk = [&](int t, int st) {
+        const uint32_t q = aQ + t * kTileBytes, k = aK + st * kTileBytes;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
-          mma_ss(tS, make_smem_desc(aQ + off, 16, 1024, 2), make_smem_desc(aK + off, 16, 1024, 2),
-                 idesc_qk, k != 0 ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+          mma_ss(tmem_base + t * 128, make_smem_desc(q + off, 16, 1024, 2),
+                 make_smem_desc(k + off, 16, 1024, 2), idesc_qk, kk != 0 ? 1u : 0u);
         }
-        tc_commit(k_empty);
-        tc_commit(s_full);
-        mbar_wait(p_full, par);
-        mbar_wait(v_full, par);
-        tc_fence_after();
+      };
+      auto issue_pv = [&](int t, int st, bool acc) {
+        const uint32_t v = aV + st * kTileBytes;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int kk = 0; kk < 8; ++kk) {
           // 16 kv rows per step: P columns advance by 8 (16 bf16), V by 16 rows x 128 B
-          mma_ts(tO, tS + k * 8, make_smem_desc(aV + k * 2048, kHalfBytes, 1024, 2), idesc_pv,
-                 (it | k) != 0 ? 1u : 0u);
+          mma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8,
+                 make_smem_desc(v + kk * 2048, kHalfBytes, 1024, 2), idesc_pv,
+                 (acc || kk != 0) ? 1u : 0u);
         }
-        tc_commit(v_empty);
-        ++it;
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      tc_commit(&s_full[0]);
+      issue_qk(1, 0);
+      tc_commit(&s_full[1]);
+      tc_commit(&k_empty[0]);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const uint32_t pj = j & 1;
+        const bool more = (j + 1 < n_kv);
+        const int st2 = (j + 1) & 1;
+        const uint32_t ph2 = ((j + 1) >> 1) & 1;
+        mbar_wait(&v_full[st], ph);
+        mbar_wait(&p_full[0], pj);
+        tc_fence_after();
+        issue_pv(0, st, j != 0);
+        if (more) {
+          mbar_wait(&k_full[st2], ph2);
+          tc_fence_after();
+          issue_qk(0, st2);
+          tc_commit(&s_full[0]);
+        }
+        mbar_wait(&p_full[1], pj);
+        tc_fence_after();
+        issue_pv(1, st, j != 0);
+        tc_commit(&v_empty[st]);
+        if (more) {
+          issue_qk(1, st2);
+          tc_commit(&s_full[1]);
+          tc_commit(&k_empty[st2]);
+        }
       }
       tc_commit(o_full);
     }
   } else {
-    // ===================== softmax / correction / epilogue =====================
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const int row = q0 + warp * 32 + lane;
-    float m_used = -INFINITY;  // running max the exponentials are referenced to (raw score units)
+    // ===================== softmax / correction / epilogue (two warpgroups) =====================
+    const int t = warp >> 2;  // query tile of this warpgroup
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + t * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + t * 128 + lane_off;
+    const int qt0 = q0 + t * kTile;
+    const int row = qt0 + (warp & 3) * 32 + lane;
+    const bool q_is_cond = (p.cond_mode != 0) && (qt0 >= p.n_main);
+    float m_used = -INFINITY;  // running reference max, log2-scaled units
     float l_sum = 0.f;
-    int it = 0;
-    for (int j = 0; j < p.kv_tiles; ++j) {
+    bool have = false;  // at least one unmasked tile seen
+    for (int j = 0; j < n_kv; ++j) {
       const bool cross = (p.cond_mode != 0) && ((j * kTile >= p.n_main) != q_is_cond);
-      if (p.cond_mode == 2 && cross) continue;
       const float bias = (p.cond_mode == 1 && cross) ? p.bias_log2 : 0.f;
-      const int kv_valid = p.n_tok - j * kTile;  // < 128 only on a ragged last tile
-      const uint32_t par = it & 1;
-      mbar_wait(s_full, par);
+      const int kv_valid = p.n_tok - j * kTile;
+      mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      // ---- pass 1: row max (in log2-scaled units)
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld_32x32(tS + lane_off + c * 32, s);
+      if (p.cond_mode == 2 && cross) {
+        // fully masked tile: P = 0, statistics untouched
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_st_32x16(tS + c * 16, z);
+      } else {
+        uint32_t s[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, s[c]);
         tmem_ld_wait();
+        if (kv_valid < kTile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(s[i]);
-          if (c * 32 + i >= kv_valid) x = -INFINITY;
-          m_tile = fmaxf(m_tile, x);
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= kv_valid) s[c][i] = 0xff800000u;  // -inf
         }
-      }
-      const float m_tile_l2 = fmaf(m_tile, p.scale_log2, bias);
-      const float m_new = fmaxf(m_used, m_tile_l2);
-      const bool need = (it == 0) || (m_new - m_used > 8.0f);
-      if (__any_sync(0xffffffffu, need)) {
-        const float alpha = (it == 0) ? 0.f : ex2_approx(m_used - m_new);
-        m_used = m_new;
-        l_sum *= alpha;
-        if (it != 0) {
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32(tO + lane_off + c * 32, o);
-            tmem_ld_wait();
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(tO + lane_off + c * 32, o);
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
+            mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
           }
-          tmem_st_wait();
-        }
-      }
-      // ---- pass 2: P = exp2(s * scale + bias - m_used) -> bf16 into TMEM (aliasing S)
-      const float neg_m = bias - m_used;
+        const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        const float m_new = fmaxf(m_used, fmaf(m_tile, p.scale_log2, bias));
+        const bool need = (!have) || (m_new - m_used > 8.0f);
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = have ? ex2_approx(m_used - m_new) : 0.f;
+          m_used = m_new;
+          l_sum *= alpha;
+          if (have) {  // `have` is warp-uniform: it only depends on the tile index
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld_32x32(tS + lane_off + c * 32, s);
-        tmem_ld_wait();
-        uint32_t pk[16];
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld_32x32(tO + c * 32, o);
+              tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x0 = __uint_as_float(s[2 * i]), x1 = __uint_as_float(s[2 * i + 1]);
-          float p0 = ex2_approx(fmaf(x0, p.scale_log2, neg_m));
-          float p1 = ex2_approx(fmaf(x1, p.scale_log2, neg_m));
-          if (c * 32 + 2 * i >= kv_valid) p0 = 0.f;
-          if (c * 32 + 2 * i + 1 >= kv_valid) p1 = 0.f;
-          l_sum += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32(tO + c * 32, o);
+            }
+          }
         }
-        tmem_st_32x16(tS + lane_off + c * 16, pk);
+        have = true;
+        const float neg_m = bias - m_used;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][2 * i]), p.scale_log2, neg_m));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][2 * i + 1]), p.scale_log2, neg_m));
+            l0 += p0;
+            l1 += p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x16(tS + c * 16, pk);
+        }
+        l_sum += l0 + l1;
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
-      ++it;
+      mbar_arrive(&p_full[t]);
     }
     // ---- epilogue: O / l -> bf16 -> HBM (token-major)
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv_l = (it > 0) ? __fdiv_rn(1.0f, l_sum) : 0.f;
+    const float inv_l = have ? __fdiv_rn(1.0f, l_sum) : 0.f;
     bf16* orow = p.out + static_cast<size_t>(row_base + row) * p.ldo + col0;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
-      if (it > 0) {
-        tmem_ld_32x32(tO + lane_off + c * 32, o);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0;
-      }
+      tmem_ld_32x32(tO + c * 32, o);
+      tmem_ld_wait();
       if (row < p.n_tok) {
         uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
@@ -271,7 +312,7 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -313,15 +354,15 @@ int attention_launch(const AttnArgs& a, cudaStream_t stream) {
   p.n_tok = a.n_tok;
   p.heads = a.heads;
   p.batch = a.batch;
-  p.q_tiles = (a.n_tok + kTile - 1) / kTile;
-  p.kv_tiles = p.q_tiles;
+  p.q_pairs = (a.n_tok + 2 * kTile - 1) / (2 * kTile);
+  p.kv_tiles = (a.n_tok + kTile - 1) / kTile;
   p.n_main = a.cond_mode ? a.n_main : a.n_tok;
   p.cond_mode = a.cond_mode;
   const float kLog2e = 1.4426950408889634f;
   p.scale_log2 = kLog2e * 0.08838834764831845f;  // 1/sqrt(128)
   p.bias_log2 = kLog2e * a.cond_bias;
   if (int rc = attention_init()) return rc;
-  const int grid = p.q_tiles * a.heads * a.batch;
+  const int grid = p.q_pairs * a.heads * a.batch;
   // algorithmic FLOPs: QK^T and PV only (4 * n^2 * 128 per head); bytes: q,k,v read + o written
   const double n = a.n_tok;
   ProfScope prof("attention", 4.0 * n * n * 128.0 * a.heads * a.batch,
