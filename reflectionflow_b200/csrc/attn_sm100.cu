@@ -34,7 +34,13 @@ struct alignas(64) AttnParamsDev {
   int n_main, cond_mode;
   float scale_log2;  // log2(e) / sqrt(128)
   float bias_log2;   // log2(e) * cond_bias
+  long long* trace;  // dev-only timeline of CTA 0 (rf_dbg_set_attn_trace); nullptr in production
 };
+
+#define RF_TR(id, j)                                                                   \
+  do {                                                                                 \
+    if (p.trace != nullptr && blockIdx.x == 0 && (j) < 24) p.trace[(j) * 16 + (id)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -175,6 +181,7 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
         const uint32_t ph2 = ((j + 1) >> 1) & 1;
         mbar_wait(&v_full[st], ph);
         mbar_wait(&p_full[0], pj);
+        RF_TR(0, j);
         tc_fence_after();
         issue_pv(0, st, j != 0);
         if (more) {
@@ -183,7 +190,9 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
           issue_qk(0, st2);
           tc_commit(&s_full[0]);
         }
+        RF_TR(1, j);
         mbar_wait(&p_full[1], pj);
+        RF_TR(2, j);
         tc_fence_after();
         issue_pv(1, st, j != 0);
         tc_commit(&v_empty[st]);
@@ -192,6 +201,7 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
           tc_commit(&s_full[1]);
           tc_commit(&k_empty[st2]);
         }
+        RF_TR(3, j);
       }
       tc_commit(o_full);
     }
@@ -212,6 +222,7 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
       const float bias = (p.cond_mode == 1 && cross) ? p.bias_log2 : 0.f;
       const int kv_valid = p.n_tok - j * kTile;
       mbar_wait(&s_full[t], j & 1);
+      if ((warp & 3) == 0 && lane == 0) RF_TR(4 + 4 * t, j);
       tc_fence_after();
       if (p.cond_mode == 2 && cross) {
         // fully masked tile: P = 0, statistics untouched
@@ -225,6 +236,7 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, s[c]);
         tmem_ld_wait();
+        if ((warp & 3) == 0 && lane == 0) RF_TR(5 + 4 * t, j);
         if (kv_valid < kTile) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -279,9 +291,11 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
         }
         l_sum += l0 + l1;
       }
+      if ((warp & 3) == 0 && lane == 0) RF_TR(6 + 4 * t, j);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      if ((warp & 3) == 0 && lane == 0) RF_TR(7 + 4 * t, j);
     }
     // ---- epilogue: O / l -> bf16 -> HBM (token-major)
     mbar_wait(o_full, 0);
@@ -315,6 +329,9 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
     tmem_dealloc<512>(tmem_base);
   }
 }
+
+static long long* g_attn_trace = nullptr;
+void dbg_set_attn_trace(long long* p) { g_attn_trace = p; }
 
 int attention_init() {
   static bool attr_set = false;
@@ -361,6 +378,7 @@ int attention_launch(const AttnArgs& a, cudaStream_t stream) {
   const float kLog2e = 1.4426950408889634f;
   p.scale_log2 = kLog2e * 0.08838834764831845f;  // 1/sqrt(128)
   p.bias_log2 = kLog2e * a.cond_bias;
+  p.trace = g_attn_trace;
   if (int rc = attention_init()) return rc;
   const int grid = p.q_pairs * a.heads * a.batch;
   // algorithmic FLOPs: QK^T and PV only (4 * n^2 * 128 per head); bytes: q,k,v read + o written

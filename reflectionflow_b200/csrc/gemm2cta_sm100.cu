@@ -1,0 +1,500 @@
+// gemm2cta_sm100.cu — the big-GEMM path: CTA-pair (tcgen05 cta_group::2) persistent bf16 GEMM.
+//
+//   out[M, N] = epilogue( A[M, K] @ W[N, K]^T ),  N % 256 == 0,  K % 64 == 0
+//
+// Same contract and epilogues as gemm_sm100.cu (which keeps serving the narrow shapes); this
+// kernel exists because a single-CTA 128x256 tile pulls 96 B/clk/SM out of L2 and a 4-stage ring
+// cannot cover the loaded L2 latency (tools/trace_gemm.py: the MMA thread waits ~40 % of a
+// K=3072 tile for TMA data).  Here two CTAs of a cluster share one 256x256 output tile:
+//   * each CTA loads its own 128 rows of A and HALF of the W tile (128 of 256 rows): 64 B/clk/SM,
+//     32 KB per stage -> a 5-stage ring;
+//   * the leader CTA issues tcgen05.mma.cta_group::2 (M = 256 across the pair, N = 256); the
+//     accumulator rows of each CTA land in its own TMEM (2 stages x 256 columns);
+//   * TMA transaction bytes of both CTAs are credited to the leader's full barrier; smem slots and
+//     accumulator stages are released with multicast tcgen05.commit.
+// Epilogue (warps 4..7 of both CTAs): TMEM -> registers -> fused math -> 128B-swizzled smem box
+// [128 rows x 64 cols] -> TMA store (coalesced, asynchronous, clips ragged M); the residual of the
+// gate+residual epilogue is prefetched by TMA one chunk ahead into smem.  Tiles are rastered in
+// 12-tile-wide column bands so a wave's W slice (19 MB at K=3072) stays L2-resident.
+#include <cuda.h>
+
+#include "rf_internal.h"
+#include "rf_ptx.cuh"
+
+namespace rf {
+
+static constexpr int kThreads2 = 256;
+static constexpr int kRows = 128;  // rows of A / of the output per CTA
+static constexpr int kBN = 256;    // pair-tile N
+static constexpr int kBK = 64;
+static constexpr int kStages = 5;
+static constexpr int kStageA = kRows * kBK * 2;        // 16 KB
+static constexpr int kStageB = (kBN / 2) * kBK * 2;    // 16 KB: this CTA's half of the W tile
+static constexpr int kStage = kStageA + kStageB;       // 32 KB
+static constexpr int kBox = kRows * 64 * 2;            // 16 KB epilogue box
+static constexpr int kSmem2 = kStages * kStage + 4 * kBox + 1024 + 512;
+static constexpr int kMaxGroups2 = 3;
+
+struct alignas(64) Gemm2Group {
+  CUtensorMap tmA, tmB, tmOut, tmRes;
+  const bf16* bias;
+  const bf16* addend;
+  const bf16* gate;
+  const float* rope_cos;
+  const float* rope_sin;
+  const bf16* norm_q;
+  const bf16* norm_k;
+  int M, ldadd, m_pairs, tile_begin;
+};
+struct alignas(64) Gemm2Params {
+  Gemm2Group g[kMaxGroups2];
+  int ngroups, N, K, n_tiles, total_tiles, num_kb, band;
+};
+
+struct Tile2 {
+  int g, m0, n0;  // m0: first row of the 256-row pair tile, n0: first column
+};
+__device__ __forceinline__ Tile2 decode2(const Gemm2Params& p, int t) {
+  int g = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxGroups2; ++i)
+    if (i < p.ngroups && t >= p.g[i].tile_begin) g = i;
+  const int local = t - p.g[g].tile_begin;
+  const int mp = p.g[g].m_pairs;
+  const int full = p.n_tiles / p.band;
+  const int full_tiles = full * mp * p.band;
+  int m, n;
+  if (local < full_tiles) {
+    const int per = mp * p.band;
+    const int sc = local / per, r = local - sc * per;
+    m = r / p.band;
+    n = sc * p.band + (r - m * p.band);
+  } else {
+    const int rem = p.n_tiles - full * p.band;
+    const int r = local - full_tiles;
+    m = r / rem;
+    n = full * p.band + (r - m * rem);
+  }
+  return Tile2{g, m * 2 * kRows, n * kBN};
+}
+
+__device__ __forceinline__ void ld8(const bf16* p, float* v) {  // 8 bf16 (16 B aligned) -> fp32
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+// v[64] = bf16(acc + bias) [ = bf16(v + addend) ]: nn.Linear (+ peft LoRA term) rounding points
+__device__ __forceinline__ void linear_round64(const uint32_t (&acc)[64], const bf16* bias,
+                                               const bf16* addend, float (&v)[64]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float b[8];
+    if (bias != nullptr) ld8(bias + q * 8, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[q * 8 + i] = bf16_round(__uint_as_float(acc[q * 8 + i]) + (bias != nullptr ? b[i] : 0.f));
+  }
+  if (addend != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float a[8];
+      ld8(addend + q * 8, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[q * 8 + i] = bf16_round(v[q * 8 + i] + a[i]);
+    }
+  }
+}
+// row r of a [128 x 64] bf16 box in the 128B-swizzled layout TMA expects
+__device__ __forceinline__ void box_store_row(uint8_t* box, int r, const float (&v)[64]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(box + r * 128 + ((q ^ (r & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void box_load_row(const uint8_t* box, int r, float (&v)[64]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint4 u = *reinterpret_cast<const uint4*>(box + r * 128 + ((q ^ (r & 7)) << 4));
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[q * 8 + 0] = a.x; v[q * 8 + 1] = a.y; v[q * 8 + 2] = b.x; v[q * 8 + 3] = b.y;
+    v[q * 8 + 4] = c.x; v[q * 8 + 5] = c.y; v[q * 8 + 6] = d.x; v[q * 8 + 7] = d.y;
+  }
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&acc)[64]) {
+  uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&acc[0]);
+  uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&acc[32]);
+  tmem_ld_32x32(taddr, lo);
+  tmem_ld_32x32(taddr + 32, hi);
+  tmem_ld_wait();
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+gemm2_kernel(const __grid_constant__ Gemm2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* out_box = smem + kStages * kStage;  // 2 boxes
+  uint8_t* res_box = out_box + 2 * kBox;       // 2 boxes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_box + 2 * kBox);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* res_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int g = 0; g < p.ngroups; ++g) {
+      tma_prefetch_desc(&p.g[g].tmA);
+      tma_prefetch_desc(&p.g[g].tmB);
+      tma_prefetch_desc(&p.g[g].tmOut);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's barrier
+      mbar_init(&res_bar[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta<512>(tmem_slot);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation of BOTH CTAs visible before any remote op
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = pair; t < p.total_tiles; t += npairs) {
+      const Tile2 tc = decode2(p, t);
+      const Gemm2Group& G = p.g[tc.g];
+      const int my_m = tc.m0 + rank * kRows;
+      const int my_n = tc.n0 + rank * (kBN / 2);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStage;
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStage);
+        tma_load_2d_2cta(sa, &G.tmA, &full_bar[stage], kb * kBK, my_m);
+        tma_load_2d_2cta(sa + kStageA, &G.tmB, &full_bar[stage], kb * kBK, my_n);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(256, kBN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = pair; t < p.total_tiles; t += npairs) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * kBN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kStage);
+        const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(sa + kStageA, 16, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          mma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        tc_commit_2cta(&empty_bar[stage], 3);  // slot free in both CTAs
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit_2cta(&tfull_bar[as], 3);  // accumulator complete in both CTAs
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs) =====================
+    const int ew = warp & 3;
+    const int r_in = ew * 32 + lane;          // row inside this CTA's 128 rows == TMEM lane
+    const bool issuer = (warp == 4 && lane == 0);
+    const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t cc = 0;  // running 64-column chunk counter (selects out_box / res_box and parities)
+
+    if constexpr (EPI == EPI_GATE_RES) {
+      if (issuer && pair < p.total_tiles) {  // residual of the first chunk of the first tile
+        const Tile2 tc = decode2(p, pair);
+        mbar_arrive_expect_tx(&res_bar[0], kBox);
+        tma_load_2d(res_box, &p.g[tc.g].tmRes, &res_bar[0], tc.n0, tc.m0 + rank * kRows);
+      }
+    }
+    for (int t = pair; t < p.total_tiles; t += npairs) {
+      const Tile2 tc = decode2(p, t);
+      const Gemm2Group& G = p.g[tc.g];
+      const int my_m = tc.m0 + rank * kRows;
+      const int row = my_m + r_in;
+      const int row_c = row < G.M ? row : G.M - 1;  // clamped row for direct global reads
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_off + as * kBN;
+
+      // issue the box store of chunk `cc` (all 128 epilogue threads call this)
+      auto publish = [&](const float (&v)[64], int col) {
+        uint8_t* ob = out_box + (cc & 1) * kBox;
+        if (issuer) tma_store_wait_read<1>();  // the store that last used this box has drained
+        named_bar_sync(1, 128);
+        box_store_row(ob, r_in, v);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          tma_store_2d(&G.tmOut, ob, col, my_m);
+          tma_store_commit();
+        }
+      };
+
+      if constexpr (EPI == EPI_QKV) {
+        const int inner = p.N / 3;
+        const float* cosr = G.rope_cos + static_cast<size_t>(row_c) * 64;
+        const float* sinr = G.rope_sin + static_cast<size_t>(row_c) * 64;
+#pragma unroll 1
+        for (int hc = 0; hc < 2; ++hc) {
+          const int col_h = tc.n0 + hc * 128;
+          const int section = col_h / inner;  // 0 q, 1 k, 2 v
+          const bf16* bias_h = G.bias ? G.bias + col_h : nullptr;
+          const bf16* add_h = G.addend ? G.addend + static_cast<size_t>(row_c) * G.ldadd + col_h : nullptr;
+          float rinv = 0.f;
+          if (section != 2) {
+            float ss = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              uint32_t acc[64];
+              tmem_ld64(taddr + hc * 128 + c * 64, acc);
+              float v[64];
+              linear_round64(acc, bias_h ? bias_h + c * 64 : nullptr, add_h ? add_h + c * 64 : nullptr, v);
+#pragma unroll
+              for (int i = 0; i < 64; ++i) ss = __fmaf_rn(v[i], v[i], ss);
+            }
+            const float var = __fdiv_rn(ss, 128.0f);
+            rinv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-6f)));
+          }
+          const bf16* nw = (section == 0) ? G.norm_q : G.norm_k;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            float cs[32], sn[32];
+            if (section != 2) {  // this row's 32 (cos, sin) pairs of the chunk; issued before the math
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(cosr + c * 32) + q);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(sinr + c * 32) + q);
+                cs[q * 4] = a.x; cs[q * 4 + 1] = a.y; cs[q * 4 + 2] = a.z; cs[q * 4 + 3] = a.w;
+                sn[q * 4] = b.x; sn[q * 4 + 1] = b.y; sn[q * 4 + 2] = b.z; sn[q * 4 + 3] = b.w;
+              }
+            }
+            uint32_t acc[64];
+            tmem_ld64(taddr + hc * 128 + c * 64, acc);
+            float v[64];
+            linear_round64(acc, bias_h ? bias_h + c * 64 : nullptr, add_h ? add_h + c * 64 : nullptr, v);
+            if (section != 2) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float w[8];
+                ld8(nw + c * 64 + q * 8, w);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float y = bf16_round(__fmul_rn(v[q * 8 + i], rinv));  // RMSNorm -> bf16
+                  v[q * 8 + i] = bf16_round(__fmul_rn(y, w[i]));              // * weight -> bf16
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {  // interleaved-pair RoPE, fp32, one rounding at the pack
+                const float x0 = v[2 * j], x1 = v[2 * j + 1];
+                v[2 * j] = __fadd_rn(__fmul_rn(x0, cs[j]), __fmul_rn(-x1, sn[j]));
+                v[2 * j + 1] = __fadd_rn(__fmul_rn(x1, cs[j]), __fmul_rn(x0, sn[j]));
+              }
+            }
+            publish(v, col_h + c * 64);
+            ++cc;
+          }
+        }
+      } else {
+        const bf16* add_r = G.addend ? G.addend + static_cast<size_t>(row_c) * G.ldadd + tc.n0 : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float r[64];
+          if constexpr (EPI == EPI_GATE_RES) {
+            // prefetch the residual of the NEXT chunk into the other box (everybody finished reading
+            // it before the barriers inside publish() of the previous chunk)
+            if (issuer) {
+              int nt = t, nc = c + 1;
+              if (nc == 4) { nt = t + npairs; nc = 0; }
+              if (nt < p.total_tiles) {
+                const Tile2 tn = decode2(p, nt);
+                const uint32_t nb = (cc + 1) & 1;
+                mbar_arrive_expect_tx(&res_bar[nb], kBox);
+                tma_load_2d(res_box + nb * kBox, &p.g[tn.g].tmRes, &res_bar[nb], tn.n0 + nc * 64,
+                            tn.m0 + rank * kRows);
+              }
+            }
+            mbar_wait(&res_bar[cc & 1], (cc >> 1) & 1);
+            box_load_row(res_box + (cc & 1) * kBox, r_in, r);
+          }
+          uint32_t acc[64];
+          tmem_ld64(taddr + c * 64, acc);
+          float v[64];
+          linear_round64(acc, G.bias ? G.bias + tc.n0 + c * 64 : nullptr,
+                         add_r ? add_r + c * 64 : nullptr, v);
+          if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = gelu_tanh(v[i]);
+          }
+          if constexpr (EPI == EPI_GATE_RES) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float gt[8];
+              ld8(G.gate + tc.n0 + c * 64 + q * 8, gt);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float gy = bf16_round(__fmul_rn(gt[i], v[q * 8 + i]));
+                v[q * 8 + i] = __fadd_rn(r[q * 8 + i], gy);
+              }
+            }
+          }
+          publish(v, tc.n0 + c * 64);
+          ++cc;
+        }
+      }
+      // release this accumulator stage: every epilogue warp of both CTAs arrives on the leader
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (issuer) tma_store_wait_all<0>();  // all boxes written to global before the kernel ends
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its pair can still touch it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+template <int EPI>
+static int set_attr2() {
+  static bool done = false;
+  if (!done) {
+    RF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSmem2));
+    done = true;
+  }
+  return 0;
+}
+int gemm2_init() {
+  return (set_attr2<EPI_BIAS>() | set_attr2<EPI_GELU>() | set_attr2<EPI_GATE_RES>() |
+          set_attr2<EPI_QKV>())
+             ? -2
+             : 0;
+}
+
+template <int EPI>
+static int launch2(const Gemm2Params& p, int pairs, double rows, cudaStream_t stream) {
+  if (int rc = set_attr2<EPI>()) return rc;
+  static const char* kNames[4] = {"gemm_bias", "gemm_gelu", "gemm_gate_res", "gemm_qkv_rms_rope"};
+  ProfScope prof(kNames[EPI], 2.0 * rows * p.N * p.K,
+                 2.0 * (rows * p.K + static_cast<double>(p.ngroups) * p.N * p.K + rows * p.N), stream);
+  gemm2_kernel<EPI><<<2 * pairs, kThreads2, kSmem2, stream>>>(p);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+bool gemm2_eligible(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups) {
+  if (N % kBN != 0 || K % kBK != 0 || ngroups > kMaxGroups2) return false;
+  if (epi == EPI_QKV && N % 384 != 0) return false;
+  for (int g = 0; g < ngroups; ++g) {
+    if (groups[g].M < 128) return false;  // tiny problems stay on the single-CTA kernel
+    if ((groups[g].ldo * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(groups[g].out) & 15)) return false;
+    if (epi == EPI_GATE_RES &&
+        ((groups[g].ldr * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(groups[g].res) & 15)))
+      return false;
+  }
+  return true;
+}
+
+int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups,
+                 cudaStream_t stream) {
+  Gemm2Params p;
+  memset(&p, 0, sizeof(p));
+  p.ngroups = ngroups;
+  p.N = N;
+  p.K = K;
+  p.n_tiles = N / kBN;
+  p.num_kb = K / kBK;
+  p.band = p.n_tiles < 12 ? p.n_tiles : 12;
+  int tiles = 0;
+  double rows = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    const GemmGroupArgs& a = groups[g];
+    Gemm2Group& d = p.g[g];
+    int rc = make_tmap_2d(&d.tmA, a.A, a.M, K, a.lda, kRows);
+    if (rc) return rc;
+    rc = make_tmap_2d(&d.tmB, a.W, N, K, K, kBN / 2);
+    if (rc) return rc;
+    rc = make_tmap_2d(&d.tmOut, a.out, a.M, N, a.ldo, kRows);
+    if (rc) return rc;
+    if (epi == EPI_GATE_RES) {
+      if (a.res == nullptr || a.gate == nullptr) {
+        set_error("gemm2_launch: EPI_GATE_RES needs res and gate");
+        return -1;
+      }
+      rc = make_tmap_2d(&d.tmRes, a.res, a.M, N, a.ldr, kRows);
+      if (rc) return rc;
+    }
+    if (epi == EPI_QKV && (!a.rope_cos || !a.rope_sin || !a.norm_q || !a.norm_k)) {
+      set_error("gemm2_launch: EPI_QKV needs rope tables and norm weights");
+      return -1;
+    }
+    d.bias = a.bias; d.addend = a.addend; d.gate = a.gate;
+    d.rope_cos = a.rope_cos; d.rope_sin = a.rope_sin; d.norm_q = a.norm_q; d.norm_k = a.norm_k;
+    d.M = a.M; d.ldadd = a.ldadd;
+    d.m_pairs = (a.M + 2 * kRows - 1) / (2 * kRows);
+    d.tile_begin = tiles;
+    tiles += d.m_pairs * p.n_tiles;
+    rows += a.M;
+  }
+  p.total_tiles = tiles;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int pairs = sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  switch (epi) {
+    case EPI_BIAS: return launch2<EPI_BIAS>(p, pairs, rows, stream);
+    case EPI_GELU: return launch2<EPI_GELU>(p, pairs, rows, stream);
+    case EPI_GATE_RES: return launch2<EPI_GATE_RES>(p, pairs, rows, stream);
+    case EPI_QKV: return launch2<EPI_QKV>(p, pairs, rows, stream);
+    default: break;
+  }
+  set_error("gemm2_launch: unknown epilogue");
+  return -1;
+}
+
+}  // namespace rf

@@ -44,6 +44,7 @@ struct alignas(64) GemmGroupDev {
 struct alignas(64) GemmParamsDev {
   GemmGroupDev g[kMaxGroups];
   int ngroups, N, K, n_tiles, total_tiles, num_kb;
+  long long* trace;  // dev-only per-tile timeline of CTA 0 (rf_dbg_set_gemm_trace)
 };
 
 template <int BN>
@@ -162,11 +163,16 @@ gemm_kernel(const __grid_constant__ GemmParamsDev p) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int ti = 0;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
       TileCoord tc = decode_tile(p, t);
       const GemmGroupDev& G = p.g[tc.g];
+      long long stall = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
+        const long long w0 = tr ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (tr) stall += clock64() - w0;
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kStageBytesA;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -174,6 +180,7 @@ gemm_kernel(const __grid_constant__ GemmParamsDev p) {
         tma_load_2d(sb, &G.tmB, &full_bar[stage], kb * BK, tc.n0 * BN);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (tr && ti < 16) p.trace[ti * 8 + 6] = stall;
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
@@ -182,12 +189,19 @@ gemm_kernel(const __grid_constant__ GemmParamsDev p) {
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int ti = 0;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+      if (tr && ti < 16) p.trace[ti * 8 + 0] = clock64();
       mbar_wait(&tempty_bar[as], aphase ^ 1);
+      if (tr && ti < 16) p.trace[ti * 8 + 1] = clock64();
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
+      long long stall = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
+        const long long w0 = tr ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);
+        if (tr) stall += clock64() - w0;
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint32_t sb = sa + Cfg::kStageBytesA;
@@ -202,6 +216,7 @@ gemm_kernel(const __grid_constant__ GemmParamsDev p) {
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
       tc_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      if (tr && ti < 16) { p.trace[ti * 8 + 2] = stall; p.trace[ti * 8 + 3] = clock64(); }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -209,13 +224,16 @@ gemm_kernel(const __grid_constant__ GemmParamsDev p) {
     const int ew = warp & 3;  // TMEM lane quadrant this warp may access
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int ti = 0;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
       TileCoord tc = decode_tile(p, t);
       const GemmGroupDev& G = p.g[tc.g];
       const int row = tc.m0 + ew * 32 + lane;
       const bool row_ok = row < G.M;
       const int ncol0 = tc.n0 * BN;
       mbar_wait(&tfull_bar[as], aphase);
+      if (tr && ti < 16) p.trace[ti * 8 + 4] = clock64();
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
 
@@ -332,6 +350,7 @@ gemm_kernel(const __grid_constant__ GemmParamsDev p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (tr && ti < 16) p.trace[ti * 8 + 5] = clock64();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -386,6 +405,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   return 0;
 }
 
+static long long* g_gemm_trace = nullptr;
+void dbg_set_gemm_trace(long long* p) { g_gemm_trace = p; }
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -409,8 +430,9 @@ static int set_attr() {
   return 0;
 }
 
+int gemm2_init();
 int gemm_init() {
-  int rc = 0;
+  int rc = gemm2_init();
   rc |= set_attr<256, EPI_BIAS>(); rc |= set_attr<256, EPI_GELU>();
   rc |= set_attr<256, EPI_GATE_RES>(); rc |= set_attr<256, EPI_QKV>();
   rc |= set_attr<128, EPI_BIAS>(); rc |= set_attr<128, EPI_GELU>();
@@ -448,8 +470,16 @@ static int launch_bn(int epi, const GemmParamsDev& p, cudaStream_t stream) {
   return -1;
 }
 
+bool gemm2_eligible(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups);
+int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups, cudaStream_t stream);
+int gemm2_init();
+static bool g_force_v1 = false;
+void dbg_force_gemm_v1(bool on) { g_force_v1 = on; }
+
 int gemm_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups,
                 cudaStream_t stream) {
+  if (ngroups >= 1 && !g_force_v1 && gemm2_eligible(epi, N, K, ngroups, groups))
+    return gemm2_launch(epi, N, K, ngroups, groups, stream);  // CTA-pair kernel for the big shapes
   if (ngroups < 1 || ngroups > kMaxGroups) {
     set_error("gemm_launch: ngroups must be 1..3");
     return -1;
@@ -502,6 +532,7 @@ int gemm_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups,
     }
   }
   p.total_tiles = tiles;
+  p.trace = g_gemm_trace;
   if (epi == EPI_QKV) {
     return bn == 256 ? launch_cfg<256, EPI_QKV>(p, stream) : launch_cfg<128, EPI_QKV>(p, stream);
   }

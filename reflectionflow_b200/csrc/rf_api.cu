@@ -39,8 +39,15 @@ ProfScope::~ProfScope() {
 }  // namespace rf
 
 using rf::bf16;
+namespace rf { void dbg_set_attn_trace(long long* p); void dbg_set_gemm_trace(long long* p); void dbg_force_gemm_v1(bool on); }
 
 extern "C" {
+
+// dev-only: timeline buffer (24 x 16 int64, device) for CTA 0 of the next attention launches
+void rf_dbg_force_gemm_v1(int on) { rf::dbg_force_gemm_v1(on != 0); }
+void rf_dbg_set_gemm_trace(void* dev_buf) { rf::dbg_set_gemm_trace(static_cast<long long*>(dev_buf)); }
+void rf_dbg_set_attn_trace(void* dev_buf) { rf::dbg_set_attn_trace(static_cast<long long*>(dev_buf)); }
+
 
 const char* rf_last_error(void) { return rf::get_error(); }
 int rf_abi_version(void) { return RF_B200_ABI_VERSION; }

@@ -54,10 +54,21 @@ def _call_linear(epi, x, W, bias, y, addend=None, res=None, gate=None, cos=None,
     torch.cuda.synchronize()
 
 
+@pytest.fixture(params=["pair", "single"])
+def gemm_path(request):
+    """big shapes run on the CTA-pair kernel (gemm2cta_sm100.cu); `single` forces the 1-CTA kernel
+    (gemm_sm100.cu) so both stay covered"""
+    lib = L.load()
+    lib.rf_dbg_force_gemm_v1(1 if request.param == "single" else 0)
+    yield request.param
+    lib.rf_dbg_force_gemm_v1(0)
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 256, 128), (200, 128, 192),
                                    (4608, 3072, 3072), (512, 3072, 4096), (4096, 64, 3072),
-                                   (1024, 12288, 3072), (768, 3072, 15360)])
-def test_linear_bias(M, N, K):
+                                   (1024, 12288, 3072), (768, 3072, 15360), (300, 512, 256),
+                                   (4608 + 77, 768, 512)])
+def test_linear_bias(M, N, K, gemm_path):
     x = _randn(M, K, seed=1)
     W = _randn(N, K, scale=1.0 / math.sqrt(K), seed=2)
     b = _randn(N, seed=3)
@@ -72,7 +83,7 @@ def test_linear_bias(M, N, K):
     assert frac_exact > 0.97
 
 
-def test_linear_no_bias_and_addend():
+def test_linear_no_bias_and_addend(gemm_path):
     M, N, K = 384, 256, 256
     x = _randn(M, K, seed=4)
     W = _randn(N, K, scale=1.0 / math.sqrt(K), seed=5)
@@ -84,7 +95,7 @@ def test_linear_no_bias_and_addend():
     torch.testing.assert_close(y.float(), ref.float(), rtol=2 ** -7, atol=2e-2)
 
 
-def test_linear_gelu():
+def test_linear_gelu(gemm_path):
     M, N, K = 640, 512, 256
     x = _randn(M, K, seed=7)
     W = _randn(N, K, scale=1.0 / math.sqrt(K), seed=8)
@@ -96,7 +107,7 @@ def test_linear_gelu():
     torch.testing.assert_close(y.float(), ref.float(), rtol=2 ** -6, atol=2e-2)
 
 
-def test_linear_gate_residual_inplace():
+def test_linear_gate_residual_inplace(gemm_path):
     M, N, K = 512, 768, 512
     x = _randn(M, K, seed=10)
     W = _randn(N, K, scale=1.0 / math.sqrt(K), seed=11)
@@ -137,8 +148,8 @@ def _qkv_ref(x, W, b, cos, sin, nq, nk, heads):
     return out
 
 
-@pytest.mark.parametrize("M,heads,K", [(256, 2, 256), (640, 24, 512)])
-def test_linear_qkv_rmsnorm_rope(M, heads, K):
+@pytest.mark.parametrize("M,heads,K", [(256, 2, 256), (640, 24, 512), (333, 4, 256)])
+def test_linear_qkv_rmsnorm_rope(M, heads, K, gemm_path):
     N = 3 * heads * 128
     x = _randn(M, K, seed=20)
     W = _randn(N, K, scale=1.0 / math.sqrt(K), seed=21)
