@@ -39,7 +39,8 @@ struct alignas(64) AttnParamsDev {
 
 #define RF_TR(id, j)                                                                   \
   do {                                                                                 \
-    if (p.trace != nullptr && blockIdx.x == 0 && (j) < 24) p.trace[(j) * 16 + (id)] = clock64(); \
+    if (p.trace != nullptr && blockIdx.x == 0 && (j) < 24 && (threadIdx.x & 31) == 0)  \
+      p.trace[(j) * 16 + (id)] = clock64();                                            \
   } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -101,7 +102,7 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 4);  // one arrive per softmax warp
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -116,84 +117,99 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
       for (int t = 0; t < 2; ++t) {
         tma_load_2d(sQ + t * kTileBytes, &p.tmQ, q_full, col0, row_base + q0 + t * kTile);
         tma_load_2d(sQ + t * kTileBytes + kHalfBytes, &p.tmQ, q_full, col0 + 64,
                     row_base + q0 + t * kTile);
       }
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t par = ((j >> 1) & 1) ^ 1;
-        uint8_t* kd = sK + st * kTileBytes;
-        uint8_t* vd = sV + st * kTileBytes;
-        mbar_wait(&k_empty[st], par);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      const uint32_t par = ((j >> 1) & 1) ^ 1;
+      uint8_t* kd = sK + st * kTileBytes;
+      uint8_t* vd = sV + st * kTileBytes;
+      mbar_wait(&k_empty[st], par);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[st], kTileBytes);
         tma_load_2d(kd, &p.tmK, &k_full[st], col0, row_base + j * kTile);
         tma_load_2d(kd + kHalfBytes, &p.tmK, &k_full[st], col0 + 64, row_base + j * kTile);
-        mbar_wait(&v_empty[st], par);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[st], par);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[st], kTileBytes);
         tma_load_2d(vd, &p.tmV, &v_full[st], col0, row_base + j * kTile);
         tma_load_2d(vd + kHalfBytes, &p.tmV, &v_full[st], col0 + 64, row_base + j * kTile);
       }
+      __syncwarp();
     }
   } else if (warp == 9) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);  // A, B K-major
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (V) MN-major
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
-      auto issue_qk = [&](int t, int st) {
-        const uint32_t q = aQ + t * kTileBytes, k = aK + st * kTileBytes;
+    // ===================== MMA issuer =====================
+    // The WHOLE warp runs this code (warp-uniform control flow keeps descriptors in uniform
+    // registers: issuing from inside `if (lane == 0)` costs ~15 SASS instructions and an
+    // ELECT/BRA loop per tcgen05.mma); one elected lane issues the MMAs and commits.
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);  // A, B K-major
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (V) MN-major
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+    auto issue_qk = [&](int t, int st) {
+      const uint32_t q = aQ + t * kTileBytes, k = aK + st * kTileBytes;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-          mma_ss(tmem_base + t * 128, make_smem_desc(q + off, 16, 1024, 2),
-                 make_smem_desc(k + off, 16, 1024, 2), idesc_qk, kk != 0 ? 1u : 0u);
-        }
-      };
-      auto issue_pv = [&](int t, int st, bool acc) {
-        const uint32_t v = aV + st * kTileBytes;
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+        mma_ss(tmem_base + t * 128, make_smem_desc(q + off, 16, 1024, 2),
+               make_smem_desc(k + off, 16, 1024, 2), idesc_qk, kk != 0 ? 1u : 0u);
+      }
+    };
+    auto issue_pv = [&](int t, int st, bool acc) {
+      const uint32_t v = aV + st * kTileBytes;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          // 16 kv rows per step: P columns advance by 8 (16 bf16), V by 16 rows x 128 B
-          mma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8,
-                 make_smem_desc(v + kk * 2048, kHalfBytes, 1024, 2), idesc_pv,
-                 (acc || kk != 0) ? 1u : 0u);
-        }
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
+      for (int kk = 0; kk < 8; ++kk) {
+        // 16 kv rows per step: P columns advance by 8 (16 bf16), V by 16 rows x 128 B
+        mma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8,
+               make_smem_desc(v + kk * 2048, kHalfBytes, 1024, 2), idesc_pv,
+               (acc || kk != 0) ? 1u : 0u);
+      }
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
       issue_qk(0, 0);
       tc_commit(&s_full[0]);
       issue_qk(1, 0);
       tc_commit(&s_full[1]);
       tc_commit(&k_empty[0]);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const uint32_t pj = j & 1;
-        const bool more = (j + 1 < n_kv);
-        const int st2 = (j + 1) & 1;
-        const uint32_t ph2 = ((j + 1) >> 1) & 1;
-        mbar_wait(&v_full[st], ph);
-        mbar_wait(&p_full[0], pj);
-        RF_TR(0, j);
-        tc_fence_after();
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const uint32_t pj = j & 1;
+      const bool more = (j + 1 < n_kv);
+      const int st2 = (j + 1) & 1;
+      const uint32_t ph2 = ((j + 1) >> 1) & 1;
+      mbar_wait(&v_full[st], ph);
+      mbar_wait(&p_full[0], pj);
+      if (more) mbar_wait(&k_full[st2], ph2);
+      RF_TR(0, j);
+      tc_fence_after();
+      if (elect_one()) {
         issue_pv(0, st, j != 0);
         if (more) {
-          mbar_wait(&k_full[st2], ph2);
-          tc_fence_after();
           issue_qk(0, st2);
           tc_commit(&s_full[0]);
         }
-        RF_TR(1, j);
-        mbar_wait(&p_full[1], pj);
-        RF_TR(2, j);
-        tc_fence_after();
+      }
+      __syncwarp();
+      RF_TR(1, j);
+      mbar_wait(&p_full[1], pj);
+      RF_TR(2, j);
+      tc_fence_after();
+      if (elect_one()) {
         issue_pv(1, st, j != 0);
         tc_commit(&v_empty[st]);
         if (more) {
@@ -201,10 +217,12 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
           tc_commit(&s_full[1]);
           tc_commit(&k_empty[st2]);
         }
-        RF_TR(3, j);
       }
-      tc_commit(o_full);
+      __syncwarp();
+      RF_TR(3, j);
     }
+    if (elect_one()) tc_commit(o_full);
+    __syncwarp();
   } else {
     // ===================== softmax / correction / epilogue (two warpgroups) =====================
     const int t = warp >> 2;  // query tile of this warpgroup
@@ -294,7 +312,8 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
       if ((warp & 3) == 0 && lane == 0) RF_TR(6 + 4 * t, j);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[t]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
       if ((warp & 3) == 0 && lane == 0) RF_TR(7 + 4 * t, j);
     }
     // ---- epilogue: O / l -> bf16 -> HBM (token-major)
