@@ -149,7 +149,26 @@ def cpu_reference_leg(steps: int, warmup: int):
             "ms_per_step": step_s * 1e3}
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout.
+    Route fd 1 to stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=STEPS_PER_IMAGE)
@@ -180,13 +199,13 @@ def main():
                 "e2e": {"value": leg["value"], "unit": "denoise-steps/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the product arm has no CPU fallback"}))
+        _emit({"error": "no CUDA device: the product arm has no CPU fallback"})
         sys.exit(2)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -320,7 +339,7 @@ def main():
     if not args.no_cpu_baseline:
         leg = cpu_reference_leg(1, 1)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+    _emit(line)
 
 
 if __name__ == "__main__":

@@ -71,9 +71,10 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
   uint64_t* v_full = bars + 5;    // [2]
   uint64_t* v_empty = bars + 7;   // [2]
   uint64_t* s_full = bars + 9;    // [2] per query tile
-  uint64_t* p_full = bars + 11;   // [2] per query tile
-  uint64_t* o_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* p_lo = bars + 11;     // [2] per query tile: P of kv rows 0..63 written
+  uint64_t* p_hi = bars + 13;     // [2] per query tile: P of kv rows 64..127 written
+  uint64_t* o_full = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,7 +103,8 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);  // one arrive per softmax warp
+      mbar_init(&p_lo[i], 4);  // one arrive per softmax warp
+      mbar_init(&p_hi[i], 4);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -132,14 +134,14 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
       const uint32_t par = ((j >> 1) & 1) ^ 1;
       uint8_t* kd = sK + st * kTileBytes;
       uint8_t* vd = sV + st * kTileBytes;
-      mbar_wait(&k_empty[st], par);
+      mbar_wait_backoff(&k_empty[st], par, 200);
       if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[st], kTileBytes);
         tma_load_2d(kd, &p.tmK, &k_full[st], col0, row_base + j * kTile);
         tma_load_2d(kd + kHalfBytes, &p.tmK, &k_full[st], col0 + 64, row_base + j * kTile);
       }
       __syncwarp();
-      mbar_wait(&v_empty[st], par);
+      mbar_wait_backoff(&v_empty[st], par, 200);
       if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[st], kTileBytes);
         tma_load_2d(vd, &p.tmV, &v_full[st], col0, row_base + j * kTile);
@@ -164,10 +166,10 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
                make_smem_desc(k + off, 16, 1024, 2), idesc_qk, kk != 0 ? 1u : 0u);
       }
     };
-    auto issue_pv = [&](int t, int st, bool acc) {
+    auto issue_pv = [&](int t, int st, bool acc, int k0) {  // k-steps [k0, k0 + 4)
       const uint32_t v = aV + st * kTileBytes;
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
+      for (int kk = k0; kk < k0 + 4; ++kk) {
         // 16 kv rows per step: P columns advance by 8 (16 bf16), V by 16 rows x 128 B
         mma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8,
                make_smem_desc(v + kk * 2048, kHalfBytes, 1024, 2), idesc_pv,
@@ -193,12 +195,16 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
       const int st2 = (j + 1) & 1;
       const uint32_t ph2 = ((j + 1) >> 1) & 1;
       mbar_wait(&v_full[st], ph);
-      mbar_wait(&p_full[0], pj);
-      if (more) mbar_wait(&k_full[st2], ph2);
+      mbar_wait(&p_lo[0], pj);
       RF_TR(0, j);
       tc_fence_after();
+      if (elect_one()) issue_pv(0, st, j != 0, 0);  // first half of P_A: overlaps the rest of A's softmax
+      __syncwarp();
+      mbar_wait(&p_hi[0], pj);
+      if (more) mbar_wait(&k_full[st2], ph2);
+      tc_fence_after();
       if (elect_one()) {
-        issue_pv(0, st, j != 0);
+        issue_pv(0, st, true, 4);
         if (more) {
           issue_qk(0, st2);
           tc_commit(&s_full[0]);
@@ -206,11 +212,15 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
       }
       __syncwarp();
       RF_TR(1, j);
-      mbar_wait(&p_full[1], pj);
+      mbar_wait(&p_lo[1], pj);
       RF_TR(2, j);
       tc_fence_after();
+      if (elect_one()) issue_pv(1, st, j != 0, 0);
+      __syncwarp();
+      mbar_wait(&p_hi[1], pj);
+      tc_fence_after();
       if (elect_one()) {
-        issue_pv(1, st, j != 0);
+        issue_pv(1, st, true, 4);
         tc_commit(&v_empty[st]);
         if (more) {
           issue_qk(1, st2);
@@ -223,7 +233,7 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
     }
     if (elect_one()) tc_commit(o_full);
     __syncwarp();
-  } else {
+  } else if (warp < 8) {
     // ===================== softmax / correction / epilogue (two warpgroups) =====================
     const int t = warp >> 2;  // query tile of this warpgroup
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -249,7 +259,12 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
         for (int i = 0; i < 16; ++i) z[i] = 0u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_st_32x16(tS + c * 16, z);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_lo[t]);
       } else {
+        // the whole 128-value score row lives in registers: one TMEM read per tile
         uint32_t s[4][32];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, s[c]);
@@ -292,28 +307,40 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
           }
         }
         have = true;
+        // P = exp2(s * scale + bias - m_used), two elements per instruction (FFMA2 / FADD2)
         const float neg_m = bias - m_used;
-        float l0 = 0.f, l1 = 0.f;
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        const float2 nm2 = make_float2(neg_m, neg_m);
+        float2 l2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][2 * i]), p.scale_log2, neg_m));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][2 * i + 1]), p.scale_log2, neg_m));
-            l0 += p0;
-            l1 += p1;
-            pk[i] = pack_bf16x2(p0, p1);
+            const float2 x = __ffma2_rn(
+                make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
+            float2 e;
+            e.x = ex2_approx(x.x);
+            e.y = ex2_approx(x.y);
+            l2 = __fadd2_rn(l2, e);
+            pk[i] = pack_bf16x2(e.x, e.y);
           }
           tmem_st_32x16(tS + c * 16, pk);
+          if (c == 1) {  // P of kv rows 0..63 complete: PV can start on it while the rest is computed
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_lo[t]);
+          }
         }
+        const float l0 = l2.x, l1 = l2.y;
         l_sum += l0 + l1;
       }
       if ((warp & 3) == 0 && lane == 0) RF_TR(6 + 4 * t, j);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (lane == 0) mbar_arrive(&p_hi[t]);
       if ((warp & 3) == 0 && lane == 0) RF_TR(7 + 4 * t, j);
     }
     // ---- epilogue: O / l -> bf16 -> HBM (token-major)
