@@ -314,9 +314,16 @@ def main():
     dom_name, dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
     # tensor-bound kernels: FLOPs / time vs the SUSTAINED measured peak (kernel timed inside a long step)
     ach = dom["flops"] / (dom["ms"] / 1e3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom_name)
     roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach,
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
-                "peak_source": pk["source"] + " (sustained cuBLAS bf16)", "traffic": None,
+                "peak_source": pk["source"] + " (sustained cuBLAS bf16)", "traffic": traffic,
+                "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture "
+                                "(profiles/ncu_traffic.json); algorithmic bytes per launch = "
+                                + str(round(dom["bytes"] / dom["launches"])),
                 "launches_per_step": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
                 "share_of_step": dom["ms"] / tot_ms,
                 "how": "CUDA events around every launch of one eager forward inside this run"}

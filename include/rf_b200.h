@@ -125,7 +125,9 @@ int rf_dit_missing_weights(rf_dit* h);
  * Builds the RoPE tables once (the reference rebuilds them every step, transformer.py:130-134)
  * and sizes the workspace.  n_cond = 0 selects entry A (stock FluxTransformer2DModel.forward);
  * n_cond > 0 selects entry B (train_flux/flux/transformer.py:47 tranformer_forward).
- * flags: bit0 latent_lora, bit1 add_cond_attn, bit2 union_cond_attn==False;
+ * flags: bit0 latent_lora, bit1 add_cond_attn, bit2 union_cond_attn==False, bit3 = apply the LoRA
+ * as merged weights W + B A for the condition tokens (peft fuse_lora semantics: one rounding of
+ * the merged weight instead of three roundings of the low-rank path; no extra launches);
  * condition_scale != 1 enables the c_factor attention bias (generate.py:86-90). */
 int rf_dit_prepare(rf_dit* h, int batch, int n_txt, int n_img, int n_cond, const void* txt_ids,
                    const void* img_ids, const void* cond_ids, int flags, float condition_scale,

@@ -26,6 +26,8 @@
 #include "rf_internal.h"
 
 namespace rf {
+int lora_merge_launch(const bf16* W, const bf16* A, const bf16* B, bf16* Wm, int N, int K, int R,
+                      cudaStream_t stream);
 int add2_launch(const bf16* a, const bf16* b, bf16* out, int n, cudaStream_t stream);
 int f32_to_bf16_launch(const float* src, bf16* dst, int n, cudaStream_t stream);
 int gemm_init();
@@ -54,18 +56,21 @@ struct LoraT {  // zero-padded rank-64 factors of one target
   int in = 0, out = 0;
   bool set = false;
 };
+// (merged weights W + B A of a whole packed projection live in the block structs: *_m)
 
 struct DoubleBlk {
   Lin qkv, add_qkv, to_out, to_add_out, ff1, ff2, ffc1, ffc2;
   bf16 *norm_q, *norm_k, *norm_added_q, *norm_added_k;
   LoraT l_norm1, l_q, l_k, l_v, l_out, l_ff2;
   bf16* qkvA = nullptr;  // [192, D] = stacked A of to_q/to_k/to_v
+  bf16 *qkv_m = nullptr, *to_out_m = nullptr, *ff2_m = nullptr;  // merged W + B A (fuse_lora mode)
 };
 struct SingleBlk {
   Lin qkv, mlp, out;
   bf16 *norm_q, *norm_k;
   LoraT l_norm, l_q, l_k, l_v, l_mlp, l_out;
   bf16* qkvA = nullptr;
+  bf16 *qkv_m = nullptr, *mlp_m = nullptr, *out_m = nullptr;
 };
 
 constexpr int kLoraPad = 64;
@@ -89,6 +94,9 @@ struct rf_dit {
   std::vector<DoubleBlk> dbl;
   std::vector<SingleBlk> sgl;
   bool any_lora = false;
+  bool lora_merged = false;   // merged copies are current
+  bool use_merged = false;    // rf_dit_prepare flag bit 3
+  bf16* x_emb_m = nullptr;
   // ---- geometry
   bool prepared = false;
   int batch = 0, n_txt = 0, n_img = 0, n_cond = 0, N = 0, n_main = 0;
@@ -354,6 +362,42 @@ int compute_cond_mod(rf_dit* h, const bf16* pooled, cudaStream_t s) {
   return 0;
 }
 
+// fuse_lora mode: merged weights for the condition-token groups (allocated on first use)
+int merge_one(rf_dit* h, const LoraT& t, const bf16* W, bf16** Wm, int rows_off, int out_total,
+              cudaStream_t s) {
+  // target occupies rows [rows_off, rows_off + t.out) of a packed [out_total, t.in] matrix
+  if (*Wm == nullptr) {
+    void* p = nullptr;
+    if (dev_alloc(h, &p, static_cast<size_t>(out_total) * t.in * 2)) return -2;
+    *Wm = static_cast<bf16*>(p);
+    RF_CHECK_CUDA(cudaMemcpyAsync(*Wm, W, static_cast<size_t>(out_total) * t.in * 2,
+                                  cudaMemcpyDeviceToDevice, s));
+  }
+  if (!t.set) return 0;
+  const size_t off = static_cast<size_t>(rows_off) * t.in;
+  return rf::lora_merge_launch(W + off, t.A, t.B, *Wm + off, t.out, t.in, kLoraPad, s);
+}
+int merge_all(rf_dit* h, cudaStream_t s) {
+  const int D = h->D;
+  if (h->l_x_emb.set || true) RF_TRY(merge_one(h, h->l_x_emb, h->x_emb.w, &h->x_emb_m, 0, D, s));
+  for (auto& b : h->dbl) {
+    RF_TRY(merge_one(h, b.l_q, b.qkv.w, &b.qkv_m, 0, 3 * D, s));
+    RF_TRY(merge_one(h, b.l_k, b.qkv.w, &b.qkv_m, D, 3 * D, s));
+    RF_TRY(merge_one(h, b.l_v, b.qkv.w, &b.qkv_m, 2 * D, 3 * D, s));
+    RF_TRY(merge_one(h, b.l_out, b.to_out.w, &b.to_out_m, 0, D, s));
+    RF_TRY(merge_one(h, b.l_ff2, b.ff2.w, &b.ff2_m, 0, D, s));
+  }
+  for (auto& b : h->sgl) {
+    RF_TRY(merge_one(h, b.l_q, b.qkv.w, &b.qkv_m, 0, 3 * D, s));
+    RF_TRY(merge_one(h, b.l_k, b.qkv.w, &b.qkv_m, D, 3 * D, s));
+    RF_TRY(merge_one(h, b.l_v, b.qkv.w, &b.qkv_m, 2 * D, 3 * D, s));
+    RF_TRY(merge_one(h, b.l_mlp, b.mlp.w, &b.mlp_m, 0, 4 * D, s));
+    RF_TRY(merge_one(h, b.l_out, b.out.w, &b.out_m, 0, D, s));
+  }
+  h->lora_merged = true;
+  return 0;
+}
+
 struct StreamRows {
   int row0, rows;
 };
@@ -377,7 +421,9 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
   if (use_cond) {
     g[1] = g[0];
     g[1].A = cond_lat; g[1].M = h->n_cond; g[1].out = rowp(X, D, S_cond.row0);
-    if (h->l_x_emb.set) {
+    if (h->use_merged) {
+      g[1].W = h->x_emb_m;
+    } else if (h->l_x_emb.set) {
       RF_TRY(lora_term(h, h->l_x_emb, cond_lat, h->cfg.in_channels, h->n_cond, h->LL, D, s));
       g[1].addend = h->LL; g[1].ldadd = D;
     }
@@ -433,7 +479,9 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       g[2].A = rowp(XN, D, S_cond.row0); g[2].M = S_cond.rows;
       g[2].out = rowp(QKV, D3, S_cond.row0);
       g[2].rope_cos = h->crope_cos; g[2].rope_sin = h->crope_sin;
-      if (b.l_q.set) {
+      if (h->use_merged) {
+        g[2].W = b.qkv_m;
+      } else if (b.l_q.set) {
         RF_TRY(lora_term_qkv(h, b.qkvA, b.l_q, b.l_k, b.l_v, g[2].A, D, S_cond.rows, h->LL, D3, s));
         g[2].addend = h->LL; g[2].ldadd = D3;
       }
@@ -456,7 +504,9 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       g[2] = g[0];
       g[2].A = rowp(ACT, D5, S_cond.row0); g[2].M = S_cond.rows;
       g[2].out = rowp(X, D, S_cond.row0); g[2].res = g[2].out; g[2].gate = mc + GATE_MSA * D;
-      if (b.l_out.set) {
+      if (h->use_merged) {
+        g[2].W = b.to_out_m;
+      } else if (b.l_out.set) {
         RF_TRY(lora_term(h, b.l_out, g[2].A, D5, S_cond.rows, h->LL, D, s));
         g[2].addend = h->LL; g[2].ldadd = D;
       }
@@ -495,7 +545,9 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       g[2] = g[0];
       g[2].A = rowp(ACT, D5, S_cond.row0) + D; g[2].M = S_cond.rows;
       g[2].out = rowp(X, D, S_cond.row0); g[2].res = g[2].out; g[2].gate = mc + GATE_MLP * D;
-      if (b.l_ff2.set) {
+      if (h->use_merged) {
+        g[2].W = b.ff2_m;
+      } else if (b.l_ff2.set) {
         RF_TRY(lora_term(h, b.l_ff2, g[2].A, D5, S_cond.rows, h->LL, D, s));
         g[2].addend = h->LL; g[2].ldadd = D;
       }
@@ -523,7 +575,9 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       g[1].A = rowp(XN, D, S_cond.row0); g[1].M = S_cond.rows;
       g[1].out = rowp(QKV, D3, S_cond.row0);
       g[1].rope_cos = h->crope_cos; g[1].rope_sin = h->crope_sin;
-      if (b.l_q.set) {
+      if (h->use_merged) {
+        g[1].W = b.qkv_m;
+      } else if (b.l_q.set) {
         RF_TRY(lora_term_qkv(h, b.qkvA, b.l_q, b.l_k, b.l_v, g[1].A, D, S_cond.rows, h->LL, D3, s));
         g[1].addend = h->LL; g[1].ldadd = D3;
       }
@@ -539,7 +593,9 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       g[1] = g[0];
       g[1].A = rowp(XN, D, S_cond.row0); g[1].M = S_cond.rows;
       g[1].out = rowp(ACT, D5, S_cond.row0) + D;
-      if (b.l_mlp.set) {
+      if (h->use_merged) {
+        g[1].W = b.mlp_m;
+      } else if (b.l_mlp.set) {
         RF_TRY(lora_term(h, b.l_mlp, g[1].A, D, S_cond.rows, h->LL, D4, s));
         g[1].addend = h->LL; g[1].ldadd = D4;
       }
@@ -558,7 +614,9 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       g[1] = g[0];
       g[1].A = rowp(ACT, D5, S_cond.row0); g[1].M = S_cond.rows;
       g[1].out = rowp(X, D, S_cond.row0); g[1].res = g[1].out; g[1].gate = mc + 2 * D;
-      if (b.l_out.set) {
+      if (h->use_merged) {
+        g[1].W = b.out_m;
+      } else if (b.l_out.set) {
         RF_TRY(lora_term(h, b.l_out, g[1].A, D5, S_cond.rows, h->LL, D, s));
         g[1].addend = h->LL; g[1].ldadd = D;
       }
@@ -612,6 +670,28 @@ __global__ void f32_to_bf16_kernel(const float* src, bf16* dst, int n) {
 }
 int f32_to_bf16_launch(const float* src, bf16* dst, int n, cudaStream_t stream) {
   f32_to_bf16_kernel<<<(n + 255) / 256, 256, 0, stream>>>(src, dst, n);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+// Wm[n, k] = bf16( W[n, k] + sum_r B[n, r] * A[r, k] ): what peft's fuse_lora / merge() produces
+__global__ void lora_merge_kernel(const bf16* __restrict__ W, const bf16* __restrict__ A,
+                                  const bf16* __restrict__ B, bf16* __restrict__ Wm, int N, int K,
+                                  int R) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r)
+    acc = fmaf(__bfloat162float(B[static_cast<size_t>(n) * R + r]),
+               __bfloat162float(A[static_cast<size_t>(r) * K + k]), acc);
+  const size_t i = static_cast<size_t>(n) * K + k;
+  Wm[i] = __float2bfloat16_rn(__bfloat162float(W[i]) + acc);
+}
+int lora_merge_launch(const bf16* W, const bf16* A, const bf16* B, bf16* Wm, int N, int K, int R,
+                      cudaStream_t stream) {
+  dim3 grid((K + 255) / 256, N);
+  lora_merge_kernel<<<grid, 256, 0, stream>>>(W, A, B, Wm, N, K, R);
   RF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -733,6 +813,7 @@ int rf_dit_set_lora(rf_dit* h, const char* module, const void* A, const void* B,
                              static_cast<size_t>(r) * 2, t.out, cudaMemcpyDeviceToDevice));
   t.set = true;
   h->any_lora = true;
+  h->lora_merged = false;
   return 0;
 }
 
@@ -790,6 +871,11 @@ int rf_dit_prepare(rf_dit* h, int batch, int n_txt, int n_img, int n_cond, const
                     h->n_cond == n_cond;
   if (same) drop_graph(h); else free_geometry(h);
   h->flags = flags;
+  h->use_merged = (flags & 8) != 0 && h->any_lora && n_cond > 0;
+  if (h->use_merged && !h->lora_merged) {
+    int mrc = merge_all(h, s);
+    if (mrc) return mrc;
+  }
   h->attn_cond_mode = mode;
   h->attn_cond_bias = bias;
   if (!same) {

@@ -263,11 +263,16 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 // GELU(tanh) evaluated in fp32 exactly as torch's CPU/CUDA "tanh" approximation does.
+// 0.5 x (1 + tanh(u)) == x * sigmoid(2u) exactly; the sigmoid form needs one ex2 and one rcp (both
+// MUFU, ~1e-7 relative) and has no cancellation for very negative u, where tanhf's 1 + tanh does.
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float kBeta = 0.7978845608028654f;  // sqrt(2/pi)
   const float kKappa = 0.044715f;
-  float inner = kBeta * (x + kKappa * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  const float u = kBeta * (x + kKappa * x * x * x);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * -2.885390081777927f));  // exp(-2u)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
 }
 
 }  // namespace rf

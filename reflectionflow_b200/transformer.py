@@ -59,6 +59,10 @@ class B200FluxTransformer2DModel:
         self._h = ctypes.c_void_p()
         self._geom_key = None
         self._geom_ids = None
+        # "exact": y = Wx + b + B(A x) with peft's three bf16 roundings (bit-faithful to the reference);
+        # "merged": condition tokens use W + BA (peft fuse_lora; the reference leaves that call
+        # commented out at tts_reflectionflow.py:506) — no extra kernels, +11.5 GB of weights.
+        self.lora_mode = "exact"
         with torch.cuda.device(self.device):
             c = _RfDitConfig(self.cfg.num_layers, self.cfg.num_single_layers,
                              self.cfg.num_attention_heads, self.cfg.in_channels,
@@ -160,12 +164,17 @@ class B200FluxTransformer2DModel:
                 L.check(-4, "init_synthetic_weights")
         return self
 
-    def load_lora(self, lora: Dict[str, Any], alpha: Optional[float] = None):
+    def load_lora(self, lora: Dict[str, Any], alpha: Optional[float] = None, mode: Optional[str] = None):
         """`lora`: {module_path: (A [r,in], B [out,r])}  or a peft/diffusers LoRA state dict with
         keys `[transformer.]<module>.lora_A.weight` / `.lora_B.weight`.  scaling = alpha / r
         (train_flux/config.yaml:50-51: r = alpha = 32 -> 1)."""
         if self.lora_rank <= 0:
             raise L.RFError("model was created with lora_rank=0")
+        if mode is not None:
+            if mode not in ("exact", "merged"):
+                raise ValueError("lora mode must be 'exact' or 'merged'")
+            self.lora_mode = mode
+            self._geom_key = None
         pairs = {}
         if lora and all(isinstance(v, (tuple, list)) for v in lora.values()):
             pairs = dict(lora)
@@ -189,10 +198,9 @@ class B200FluxTransformer2DModel:
         return self
 
     # ------------------------------------------------------------------ geometry
-    @staticmethod
-    def _flags(model_config: Optional[Dict[str, Any]]) -> int:
+    def _flags(self, model_config: Optional[Dict[str, Any]]) -> int:
         mc = model_config or {}
-        f = 0
+        f = 8 if self.lora_mode == "merged" else 0
         if mc.get("latent_lora", False):
             f |= 1
         if mc.get("add_cond_attn", False):

@@ -92,6 +92,28 @@ def test_dit_matches_reference_golden(name):
     assert d.mean() <= 2.0 * e_ref.mean() + 1e-3
 
 
+@pytest.mark.parametrize("name", ["fwdB_small", "fwdB_full", "denoiseB_small"])
+def test_merged_lora_mode_stays_inside_the_error_budget(name):
+    """lora_mode='merged' (peft fuse_lora semantics: condition tokens use bf16(W + BA)) is the fast
+    path of the tts loop; it changes three roundings of the low-rank path into one rounding of the
+    merged weight, so it is checked against the same fp32 truth with the same budget."""
+    case = C.CASES[name]
+    gold, _ = _golden()
+    m = _build(case)
+    _, lora = C.build_model(case)
+    m.load_lora(lora, mode="merged")
+    try:
+        ours = _run_cuda(case).float()
+    finally:
+        m.load_lora(lora, mode="exact")
+    true32, ref = gold[name + "/fp32"].float(), gold[name + "/bf16"].float()
+    e_ours, e_ref = (ours - true32).abs(), (ref - true32).abs()
+    print(f"[{name} merged] |ours-fp32| mean {e_ours.mean():.4g} max {e_ours.max():.4g} ; "
+          f"|ref-fp32| mean {e_ref.mean():.4g} max {e_ref.max():.4g}")
+    assert e_ours.mean() <= 1.3 * e_ref.mean() + 1e-3
+    assert e_ours.max() <= 2.5 * e_ref.max() + 1e-2
+
+
 def test_entry_a_forward_surface_and_determinism():
     """pipe.transformer(...) keyword surface (diffusers forward), return_dict both ways, and
     run-to-run bit determinism of the CUDA path."""
