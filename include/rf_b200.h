@@ -150,6 +150,24 @@ int rf_dit_denoise(rf_dit* h, void* latents_inout, const void* txt, const void* 
                    const uint16_t* timesteps_bf16_host, const float* sigmas_host, int n_steps,
                    float guidance_scale, const void* cond_latents, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * FLUX VAE decoder (next-tier row: `vae.decode` + `image_processor.postprocess`,
+ * train_flux/flux/generate.py:302-307).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct rf_vae rf_vae;
+int rf_vae_create(rf_vae** out);
+void rf_vae_destroy(rf_vae* h);
+/* diffusers AutoencoderKL state-dict keys of the DECODER ("decoder.conv_in.weight", ...,
+ * torch conv layout [Cout, Cin, kh, kw]); src = device bf16. */
+int rf_vae_load_weight(rf_vae* h, const char* key, const void* src, int64_t numel);
+int rf_vae_missing_weights(rf_vae* h);
+/* packed latents [(H/16)(W/16), 64] bf16 (one image) -> image.  Applies
+ * `latents / scaling_factor + shift_factor` (bf16 ops), the decoder, and
+ * VaeImageProcessor.postprocess: out_u8_hwc [H, W, 3] uint8 and/or out_bf16_chw [3, H, W] bf16
+ * (either may be NULL).  width % 1024 == 0, height % 16 == 0. */
+int rf_vae_decode(rf_vae* h, const void* packed_latents, int height, int width, float scaling_factor,
+                  float shift_factor, uint8_t* out_u8_hwc, void* out_bf16_chw, void* stream);
+
 /* Per-kernel timing of everything launched between start and stop (CUDA events on the launching
  * stream around each launch; graph-captured launches are skipped).  rf_profile_stop synchronises
  * the device and writes a JSON object {kernel: {launches, ms, flops, bytes}} (algorithmic FLOPs /

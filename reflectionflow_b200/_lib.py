@@ -44,6 +44,17 @@ def _declare(lib):
     lib.rf_op_euler_step.argtypes = [vp, vp, vp, vp, ci, vp]
     lib.rf_dbg_force_gemm_v1.restype = None
     lib.rf_dbg_force_gemm_v1.argtypes = [ci]
+    if hasattr(lib, "rf_vae_create"):
+        lib.rf_vae_create.restype = ci
+        lib.rf_vae_create.argtypes = [POINTER(vp)]
+        lib.rf_vae_destroy.restype = None
+        lib.rf_vae_destroy.argtypes = [vp]
+        lib.rf_vae_load_weight.restype = ci
+        lib.rf_vae_load_weight.argtypes = [vp, c_char_p, vp, c_int64]
+        lib.rf_vae_missing_weights.restype = ci
+        lib.rf_vae_missing_weights.argtypes = [vp]
+        lib.rf_vae_decode.restype = ci
+        lib.rf_vae_decode.argtypes = [vp, vp, ci, ci, cf, cf, vp, vp, vp]
     if hasattr(lib, "rf_dit_create"):
         lib.rf_dit_create.restype = ci
         lib.rf_dit_create.argtypes = [vp, POINTER(vp)]

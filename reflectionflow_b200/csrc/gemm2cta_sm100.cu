@@ -25,15 +25,17 @@ namespace rf {
 
 static constexpr int kThreads2 = 256;
 static constexpr int kRows = 128;  // rows of A / of the output per CTA
-static constexpr int kBN = 256;    // pair-tile N
 static constexpr int kBK = 64;
-static constexpr int kStages = 5;
 static constexpr int kStageA = kRows * kBK * 2;        // 16 KB
-static constexpr int kStageB = (kBN / 2) * kBK * 2;    // 16 KB: this CTA's half of the W tile
-static constexpr int kStage = kStageA + kStageB;       // 32 KB
 static constexpr int kBox = kRows * 64 * 2;            // 16 KB epilogue box
-static constexpr int kSmem2 = kStages * kStage + 4 * kBox + 1024 + 512;
 static constexpr int kMaxGroups2 = 3;
+template <int BN>  // pair-tile N: 256 (DiT projections, wide convs) or 128 (128-channel convs)
+struct Cfg2 {
+  static constexpr int kStageB = (BN / 2) * kBK * 2;   // this CTA's half of the W tile
+  static constexpr int kStage = kStageA + kStageB;     // 32 KB / 24 KB
+  static constexpr int kStages = (BN == 256) ? 5 : 6;
+  static constexpr int kSmem = kStages * kStage + 4 * kBox + 1024 + 512;
+};
 
 struct alignas(64) Gemm2Group {
   CUtensorMap tmA, tmB, tmOut, tmRes;
@@ -45,11 +47,20 @@ struct alignas(64) Gemm2Group {
   const bf16* norm_q;
   const bf16* norm_k;
   int M, ldadd, m_pairs, tile_begin;
+  // implicit-GEMM convolution over a zero-padded NHWC image [(H+2) * (W+2), C] (conv_w > 0):
+  // output row m = y * W + x; tap t of k-block kb reads input row (y+1+dy) * (W+2) + x+1+dx
+  int conv_w, conv_taps, conv_cin_blocks;
 };
 struct alignas(64) Gemm2Params {
   Gemm2Group g[kMaxGroups2];
-  int ngroups, N, K, n_tiles, total_tiles, num_kb, band;
+  int ngroups, N, K, n_tiles, total_tiles, num_kb, band, bn;
 };
+// padded-image row of output pixel m (identity for a plain GEMM)
+__device__ __forceinline__ int out_row(const Gemm2Group& G, int m) {
+  if (G.conv_w == 0) return m;
+  const int y = m / G.conv_w, x = m - y * G.conv_w;
+  return (y + 1) * (G.conv_w + 2) + x + 1;
+}
 
 struct Tile2 {
   int g, m0, n0;  // m0: first row of the 256-row pair tile, n0: first column
@@ -75,7 +86,7 @@ __device__ __forceinline__ Tile2 decode2(const Gemm2Params& p, int t) {
     m = r / rem;
     n = full * p.band + (r - m * rem);
   }
-  return Tile2{g, m * 2 * kRows, n * kBN};
+  return Tile2{g, m * 2 * kRows, n * p.bn};
 }
 
 __device__ __forceinline__ void ld8(const bf16* p, float* v) {  // 8 bf16 (16 B aligned) -> fp32
@@ -133,9 +144,11 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&acc)[64]) {
   tmem_ld_wait();
 }
 
-template <int EPI>
+template <int EPI, int kBN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_kernel(const __grid_constant__ Gemm2Params p) {
+  constexpr int kStages = Cfg2<kBN>::kStages;
+  constexpr int kStage = Cfg2<kBN>::kStage;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -175,7 +188,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc_2cta<512>(tmem_slot);
+    tmem_alloc_2cta<2 * kBN>(tmem_slot);
     tmem_relinquish_2cta();
   }
   tc_fence_before();
@@ -192,11 +205,19 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       const Gemm2Group& G = p.g[tc.g];
       const int my_m = tc.m0 + rank * kRows;
       const int my_n = tc.n0 + rank * (kBN / 2);
+      const int a_row0 = out_row(G, my_m);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * kStage;
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStage);
-        tma_load_2d_2cta(sa, &G.tmA, &full_bar[stage], kb * kBK, my_m);
+        int a_row = my_m, a_col = kb * kBK;
+        if (G.conv_w != 0) {
+          const int tap = kb / G.conv_cin_blocks;
+          a_col = (kb - tap * G.conv_cin_blocks) * kBK;
+          a_row = a_row0;
+          if (G.conv_taps == 9) a_row += (tap / 3 - 1) * (G.conv_w + 2) + (tap % 3 - 1);
+        }
+        tma_load_2d_2cta(sa, &G.tmA, &full_bar[stage], a_col, a_row);
         tma_load_2d_2cta(sa + kStageA, &G.tmB, &full_bar[stage], kb * kBK, my_n);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -241,7 +262,8 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       if (issuer && pair < p.total_tiles) {  // residual of the first chunk of the first tile
         const Tile2 tc = decode2(p, pair);
         mbar_arrive_expect_tx(&res_bar[0], kBox);
-        tma_load_2d(res_box, &p.g[tc.g].tmRes, &res_bar[0], tc.n0, tc.m0 + rank * kRows);
+        tma_load_2d(res_box, &p.g[tc.g].tmRes, &res_bar[0], tc.n0,
+                    out_row(p.g[tc.g], tc.m0 + rank * kRows));
       }
     }
     for (int t = pair; t < p.total_tiles; t += npairs) {
@@ -263,12 +285,13 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (issuer) {
-          tma_store_2d(&G.tmOut, ob, col, my_m);
+          tma_store_2d(&G.tmOut, ob, col, out_row(G, my_m));
           tma_store_commit();
         }
       };
 
       if constexpr (EPI == EPI_QKV) {
+        static_assert(EPI != EPI_QKV || kBN == 256, "QKV epilogue needs two heads per tile");
         const int inner = p.N / 3;
         const float* cosr = G.rope_cos + static_cast<size_t>(row_c) * 64;
         const float* sinr = G.rope_sin + static_cast<size_t>(row_c) * 64;
@@ -335,20 +358,20 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       } else {
         const bf16* add_r = G.addend ? G.addend + static_cast<size_t>(row_c) * G.ldadd + tc.n0 : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kBN / 64; ++c) {
           float r[64];
           if constexpr (EPI == EPI_GATE_RES) {
             // prefetch the residual of the NEXT chunk into the other box (everybody finished reading
             // it before the barriers inside publish() of the previous chunk)
             if (issuer) {
               int nt = t, nc = c + 1;
-              if (nc == 4) { nt = t + npairs; nc = 0; }
+              if (nc == kBN / 64) { nt = t + npairs; nc = 0; }
               if (nt < p.total_tiles) {
                 const Tile2 tn = decode2(p, nt);
                 const uint32_t nb = (cc + 1) & 1;
                 mbar_arrive_expect_tx(&res_bar[nb], kBox);
                 tma_load_2d(res_box + nb * kBox, &p.g[tn.g].tmRes, &res_bar[nb], tn.n0 + nc * 64,
-                            tn.m0 + rank * kRows);
+                            out_row(p.g[tn.g], tn.m0 + rank * kRows));
               }
             }
             mbar_wait(&res_bar[cc & 1], (cc >> 1) & 1);
@@ -392,42 +415,45 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
   cluster_sync_all();  // no CTA may exit (or free TMEM) while its pair can still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc_2cta<512>(tmem_base);
+    tmem_dealloc_2cta<2 * kBN>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------ host
-template <int EPI>
+template <int EPI, int BN>
 static int set_attr2() {
   static bool done = false;
   if (!done) {
-    RF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kSmem2));
+    RF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI, BN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmem));
     done = true;
   }
   return 0;
 }
 int gemm2_init() {
-  return (set_attr2<EPI_BIAS>() | set_attr2<EPI_GELU>() | set_attr2<EPI_GATE_RES>() |
-          set_attr2<EPI_QKV>())
+  return (set_attr2<EPI_BIAS, 256>() | set_attr2<EPI_GELU, 256>() | set_attr2<EPI_GATE_RES, 256>() |
+          set_attr2<EPI_QKV, 256>() | set_attr2<EPI_BIAS, 128>() | set_attr2<EPI_GATE_RES, 128>())
              ? -2
              : 0;
 }
 
-template <int EPI>
+template <int EPI, int BN>
 static int launch2(const Gemm2Params& p, int pairs, double rows, cudaStream_t stream) {
-  if (int rc = set_attr2<EPI>()) return rc;
+  if (int rc = set_attr2<EPI, BN>()) return rc;
   static const char* kNames[4] = {"gemm_bias", "gemm_gelu", "gemm_gate_res", "gemm_qkv_rms_rope"};
-  ProfScope prof(kNames[EPI], 2.0 * rows * p.N * p.K,
-                 2.0 * (rows * p.K + static_cast<double>(p.ngroups) * p.N * p.K + rows * p.N), stream);
-  gemm2_kernel<EPI><<<2 * pairs, kThreads2, kSmem2, stream>>>(p);
+  const char* name = p.g[0].conv_w ? (EPI == EPI_GATE_RES ? "conv_res" : "conv_bias") : kNames[EPI];
+  ProfScope prof(name, 2.0 * rows * p.N * p.K,
+                 2.0 * (rows * p.K / (p.g[0].conv_w ? p.g[0].conv_taps : 1) +
+                        static_cast<double>(p.ngroups) * p.N * p.K + rows * p.N),
+                 stream);
+  gemm2_kernel<EPI, BN><<<2 * pairs, kThreads2, Cfg2<BN>::kSmem, stream>>>(p);
   RF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 
 bool gemm2_eligible(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups) {
-  if (N % kBN != 0 || K % kBK != 0 || ngroups > kMaxGroups2) return false;
+  if (N % 256 != 0 || K % kBK != 0 || ngroups > kMaxGroups2) return false;
   if (epi == EPI_QKV && N % 384 != 0) return false;
   for (int g = 0; g < ngroups; ++g) {
     if (groups[g].M < 128) return false;  // tiny problems stay on the single-CTA kernel
@@ -439,6 +465,30 @@ bool gemm2_eligible(int epi, int N, int K, int ngroups, const GemmGroupArgs* gro
   return true;
 }
 
+static int gemm2_dispatch(int epi, Gemm2Params& p, int tiles, double rows, cudaStream_t stream) {
+  p.total_tiles = tiles;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int pairs = sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  if (p.bn == 128) {
+    if (epi == EPI_BIAS) return launch2<EPI_BIAS, 128>(p, pairs, rows, stream);
+    if (epi == EPI_GATE_RES) return launch2<EPI_GATE_RES, 128>(p, pairs, rows, stream);
+    set_error("gemm2: 128-wide tiles support the bias and residual epilogues only");
+    return -1;
+  }
+  switch (epi) {
+    case EPI_BIAS: return launch2<EPI_BIAS, 256>(p, pairs, rows, stream);
+    case EPI_GELU: return launch2<EPI_GELU, 256>(p, pairs, rows, stream);
+    case EPI_GATE_RES: return launch2<EPI_GATE_RES, 256>(p, pairs, rows, stream);
+    case EPI_QKV: return launch2<EPI_QKV, 256>(p, pairs, rows, stream);
+    default: break;
+  }
+  set_error("gemm2_launch: unknown epilogue");
+  return -1;
+}
+
 int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups,
                  cudaStream_t stream) {
   Gemm2Params p;
@@ -446,7 +496,8 @@ int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups
   p.ngroups = ngroups;
   p.N = N;
   p.K = K;
-  p.n_tiles = N / kBN;
+  p.bn = 256;
+  p.n_tiles = N / p.bn;
   p.num_kb = K / kBK;
   p.band = p.n_tiles < 12 ? p.n_tiles : 12;
   int tiles = 0;
@@ -456,7 +507,7 @@ int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups
     Gemm2Group& d = p.g[g];
     int rc = make_tmap_2d(&d.tmA, a.A, a.M, K, a.lda, kRows);
     if (rc) return rc;
-    rc = make_tmap_2d(&d.tmB, a.W, N, K, K, kBN / 2);
+    rc = make_tmap_2d(&d.tmB, a.W, N, K, K, p.bn / 2);
     if (rc) return rc;
     rc = make_tmap_2d(&d.tmOut, a.out, a.M, N, a.ldo, kRows);
     if (rc) return rc;
@@ -480,21 +531,49 @@ int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups
     tiles += d.m_pairs * p.n_tiles;
     rows += a.M;
   }
-  p.total_tiles = tiles;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int pairs = sms / 2;
-  if (pairs > tiles) pairs = tiles;
-  switch (epi) {
-    case EPI_BIAS: return launch2<EPI_BIAS>(p, pairs, rows, stream);
-    case EPI_GELU: return launch2<EPI_GELU>(p, pairs, rows, stream);
-    case EPI_GATE_RES: return launch2<EPI_GATE_RES>(p, pairs, rows, stream);
-    case EPI_QKV: return launch2<EPI_QKV>(p, pairs, rows, stream);
-    default: break;
+  return gemm2_dispatch(epi, p, tiles, rows, stream);
+}
+
+// 3x3 (taps = 9) or 1x1 (taps = 1) convolution, stride 1, zero padding, NHWC bf16 with a one-pixel
+// zero ring: in [(H+2)(W+2), Cin], out [(H+2)(W+2), Cout] (interior written, ring untouched),
+// weights [Cout, taps * Cin] (tap-major K), optional residual res[(H+2)(W+2), Cout] added after the
+// bias rounding (ResnetBlock2D: x + conv2(...)).  W % 128 == 0, Cin % 64 == 0, Cout % 128 == 0.
+int conv_launch(const bf16* in, const bf16* weight, const bf16* bias, bf16* out, const bf16* res,
+                const bf16* ones, int H, int W, int Cin, int Cout, int taps, cudaStream_t stream) {
+  if (W % 128 != 0 || Cin % 64 != 0 || Cout % 128 != 0 || (taps != 9 && taps != 1)) {
+    set_error("conv_launch: need W % 128 == 0, Cin % 64 == 0, Cout % 128 == 0, taps in {1, 9}");
+    return -1;
   }
-  set_error("gemm2_launch: unknown epilogue");
-  return -1;
+  Gemm2Params p;
+  memset(&p, 0, sizeof(p));
+  p.ngroups = 1;
+  p.N = Cout;
+  p.K = taps * Cin;
+  p.bn = (Cout % 256 == 0) ? 256 : 128;
+  p.n_tiles = Cout / p.bn;
+  p.num_kb = p.K / kBK;
+  p.band = p.n_tiles;
+  Gemm2Group& d = p.g[0];
+  const uint64_t prow = static_cast<uint64_t>(H + 2) * (W + 2);
+  int rc = make_tmap_2d(&d.tmA, in, prow, Cin, Cin, kRows);
+  if (rc) return rc;
+  rc = make_tmap_2d(&d.tmB, weight, Cout, p.K, p.K, p.bn / 2);
+  if (rc) return rc;
+  rc = make_tmap_2d(&d.tmOut, out, prow, Cout, Cout, kRows);
+  if (rc) return rc;
+  if (res) {
+    rc = make_tmap_2d(&d.tmRes, res, prow, Cout, Cout, kRows);
+    if (rc) return rc;
+  }
+  d.bias = bias;
+  d.gate = ones;  // residual epilogue = bf16(res + bf16(1 * y))
+  d.M = H * W;
+  d.m_pairs = (d.M + 2 * kRows - 1) / (2 * kRows);
+  d.conv_w = W;
+  d.conv_taps = taps;
+  d.conv_cin_blocks = Cin / kBK;
+  return gemm2_dispatch(res ? EPI_GATE_RES : EPI_BIAS, p, d.m_pairs * p.n_tiles,
+                        static_cast<double>(d.M), stream);
 }
 
 }  // namespace rf

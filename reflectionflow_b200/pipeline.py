@@ -101,12 +101,17 @@ class B200FluxPipeline:
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def from_synthetic(cls, config=None, seed: int = 0, device="cuda:0", lora_rank: int = 0):
-        """Random-init FLUX.1-dev-shaped DiT (no checkpoints exist offline)."""
+    def from_synthetic(cls, config=None, seed: int = 0, device="cuda:0", lora_rank: int = 0,
+                       with_vae: bool = False):
+        """Random-init FLUX.1-dev-shaped DiT (+ VAE decoder) — no checkpoints exist offline."""
         t = B200FluxTransformer2DModel(FluxDiTConfig.from_any(config or FluxDiTConfig()),
                                        lora_rank=lora_rank, device=device)
         t.init_synthetic_weights(seed)
-        return cls(t)
+        vae = None
+        if with_vae:
+            from .vae import B200AutoencoderKL
+            vae = B200AutoencoderKL(device).init_synthetic_weights(seed + 1)
+        return cls(t, vae=vae)
 
     @classmethod
     def from_state_dict(cls, state_dict, config=None, device="cuda:0", lora_rank: int = 0):
@@ -270,11 +275,18 @@ class B200FluxPipeline:
         else:
             if self.vae is None:
                 raise NotImplementedError(
-                    "VAE decode is not native yet (SURVEY.md §8f): call with output_type='latent'")
-            x = self._unpack_latents(latents, height, width, self.vae_scale_factor)
-            x = (x / self.vae.config.scaling_factor) + self.vae.config.shift_factor
-            image = self.vae.decode(x, return_dict=False)[0]
-            image = self.image_processor.postprocess(image, output_type=output_type)
+                    "no VAE attached: call with output_type='latent' or construct the pipeline with "
+                    "vae=B200AutoencoderKL(...)")
+            # generate.py:302-307 in one device call: unpack, / scaling + shift, decode, postprocess
+            if output_type == "pil":
+                from .vae import to_pil
+                image = to_pil(self.vae.decode_packed(latents, height, width, "u8"))
+            elif output_type == "np":
+                image = self.vae.decode_packed(latents, height, width, "u8").cpu().numpy().astype("float32") / 255.0
+            elif output_type == "pt":
+                image = self.vae.decode_packed(latents, height, width, "pt")
+            else:
+                raise ValueError(f"output_type {output_type!r} not supported")
         if not return_dict:
             return (image,)
         return FluxPipelineOutput(images=image)

@@ -1,0 +1,65 @@
+"""-m gpu: native FLUX VAE decoder (rf_vae_decode) vs the CPU oracle (oracle/vae_oracle.py, restated
+diffusers AutoencoderKL) on seeded weights and latents.  The decoder is bf16 end to end like the
+reference; GroupNorm statistics, conv summation order and the materialised bf16 attention scores
+differ in rounding only, so the pre-quantisation image must agree to ~1e-2 and the uint8 image to a
+couple of LSBs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vae_oracle as vo  # noqa: E402
+from oracle import flux_oracle as fo  # noqa: E402
+from reflectionflow_b200.vae import B200AutoencoderKL  # noqa: E402
+
+_CACHE = {}
+
+
+def _models():
+    if not _CACHE:
+        torch.manual_seed(0)
+        ref = vo.AutoencoderKL()
+        vo.init_weights_(ref, seed=0)
+        ref.eval()
+        ours = B200AutoencoderKL().load_state_dict(ref.state_dict())
+        _CACHE["m"] = (ref, ours)
+    return _CACHE["m"]
+
+
+@pytest.mark.parametrize("height", [64, 128])
+def test_decode_matches_oracle(height):
+    width = 1024
+    ref, ours = _models()
+    g = torch.Generator().manual_seed(height)
+    packed = torch.randn(1, (height // 16) * (width // 16), 64, generator=g).to(torch.bfloat16)
+    img_pt = ours.decode_packed(packed, height, width, "pt")
+    img_u8 = ours.decode_packed(packed, height, width, "u8")
+    torch.cuda.synchronize()
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    want = vo.decode_latents(ref, packed, height, width)            # bf16 [1, 3, H, W]
+    want32 = vo.decode_latents(ref.float(), packed.float(), height, width)
+    ref.to(torch.bfloat16)
+    d = (img_pt.cpu().float() - want.float()).abs()
+    e_ref = (want.float() - want32).abs()
+    e_ours = (img_pt.cpu().float() - want32).abs()
+    print(f"[vae {height}x{width}] |ours-ref_bf16| mean {d.mean():.4g} max {d.max():.4g} ; "
+          f"|ref-fp32| mean {e_ref.mean():.4g} ; |ours-fp32| mean {e_ours.mean():.4g} ; "
+          f"absmax {want.float().abs().max():.3g}")
+    assert torch.isfinite(img_pt.float()).all()
+    assert e_ours.mean() <= 1.5 * e_ref.mean() + 2e-3
+    assert d.mean() <= 3.0 * e_ref.mean() + 2e-3
+    u8_want = vo.postprocess_uint8(want)
+    du = (img_u8.cpu().int() - u8_want.int()).abs()
+    print(f"  uint8: exact {float((du == 0).float().mean()):.3f}, <=1 {float((du <= 1).float().mean()):.3f}, "
+          f"max {int(du.max())}")
+    assert (du <= 2).float().mean() > 0.99
+
+
+def test_postprocess_is_bit_exact_on_given_image():
+    """the uint8 conversion itself (x/2+0.5 in bf16, clamp, *255, round-half-even) is exact: feed the
+    oracle's own pre-quantisation image through the same formula"""
+    x = torch.linspace(-1.5, 1.5, 4096).to(torch.bfloat16).view(1, 1, 64, 64).expand(1, 3, 64, 64)
+    want = vo.postprocess_uint8(x)
+    t = (x / 2 + 0.5).clamp(0, 1).float()
+    got = torch.round(t * 255).to(torch.uint8).permute(0, 2, 3, 1)
+    assert torch.equal(want, got)
