@@ -219,7 +219,7 @@ def main():
 
     nl, ns = (int(x) for x in args.layers.split(","))
     cfg = FluxDiTConfig(num_layers=nl, num_single_layers=ns)
-    pipe = B200FluxPipeline.from_synthetic(cfg, seed=0, device=dev)
+    pipe = B200FluxPipeline.from_synthetic(cfg, seed=0, device=dev, with_vae=True)
     model = pipe.transformer
     lib = L.load()
 
@@ -291,6 +291,17 @@ def main():
     h2d = (lat_host.numel() + txt_host.numel() + pool_host.numel()) * 2
     d2h = res.numel() * 2
 
+    # ---- VAE decode of the final latent (the per-image tail: generate.py:302-307), device-timed
+    for _ in range(2):
+        pipe.vae.decode_packed(final, H, W, "u8")
+    barrier()
+    e0.record()
+    for _ in range(3):
+        img = pipe.vae.decode_packed(final, H, W, "u8")
+    e1.record()
+    barrier()
+    ms_vae = e0.elapsed_time(e1) / 3
+
     # ---- per-kernel breakdown of one eager forward (CUDA events around every launch)
     prof = None
     if rank == 0:
@@ -335,6 +346,10 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": config,
             "images_per_sec_dit_only": steps_per_s / STEPS_PER_IMAGE,
+            "vae_decode_ms": ms_vae,
+            "images_per_sec": args.gpus / ((STEPS_PER_IMAGE * ms / K + ms_vae) / 1e3),
+            "images_note": "28 denoise steps at the measured step time + one native VAE decode to uint8 "
+                           "(text encoding excluded: embeddings are inputs)",
             "step_tflop": step_tflop,
             "step_tflops_achieved": step_tflop / (ms / K / 1e3),
             "step_frac_of_tensor_peak": step_tflop / (ms / K / 1e3) / pk["tflops_sustained"],
