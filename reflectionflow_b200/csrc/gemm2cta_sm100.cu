@@ -47,21 +47,22 @@ struct alignas(64) Gemm2Group {
   const bf16* norm_q;
   const bf16* norm_k;
   int M, ldadd, m_pairs, tile_begin;
-  // implicit-GEMM convolution over a zero-padded NHWC image [(H+2) * (W+2), C] (conv_w > 0):
-  // output row m = y * W + x; tap t of k-block kb reads input row (y+1+dy) * (W+2) + x+1+dx
-  int conv_w, conv_taps, conv_cin_blocks;
+  // implicit-GEMM convolution over zero-ringed NHWC images (conv_w > 0; tmA/tmOut/tmRes are 3-D maps
+  // {C, W+2, H+2}): an M tile is conv_by rows x conv_bx columns of OUTPUT pixels (bx * by = 128);
+  // tap (ky, kx) of a k-block reads input pixels (s*y + ky + s-1, s*x + kx + s-1), s = conv_stride
+  int conv_w, conv_taps, conv_cin_blocks, conv_bx, conv_by, conv_stride;
 };
+struct PixTile { int x0, y0; };
+__device__ __forceinline__ PixTile pix_tile(const Gemm2Group& G, int m) {
+  const int mt = m >> 7;                 // 128-pixel tile index
+  const int xt = G.conv_w / G.conv_bx;   // tiles per image row
+  const int ty = mt / xt;
+  return PixTile{(mt - ty * xt) * G.conv_bx, ty * G.conv_by};
+}
 struct alignas(64) Gemm2Params {
   Gemm2Group g[kMaxGroups2];
   int ngroups, N, K, n_tiles, total_tiles, num_kb, band, bn;
 };
-// padded-image row of output pixel m (identity for a plain GEMM)
-__device__ __forceinline__ int out_row(const Gemm2Group& G, int m) {
-  if (G.conv_w == 0) return m;
-  const int y = m / G.conv_w, x = m - y * G.conv_w;
-  return (y + 1) * (G.conv_w + 2) + x + 1;
-}
-
 struct Tile2 {
   int g, m0, n0;  // m0: first row of the 256-row pair tile, n0: first column
 };
@@ -205,19 +206,22 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       const Gemm2Group& G = p.g[tc.g];
       const int my_m = tc.m0 + rank * kRows;
       const int my_n = tc.n0 + rank * (kBN / 2);
-      const int a_row0 = out_row(G, my_m);
+      PixTile pt{0, 0};
+      if (G.conv_w != 0) pt = pix_tile(G, my_m);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * kStage;
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStage);
-        int a_row = my_m, a_col = kb * kBK;
         if (G.conv_w != 0) {
           const int tap = kb / G.conv_cin_blocks;
-          a_col = (kb - tap * G.conv_cin_blocks) * kBK;
-          a_row = a_row0;
-          if (G.conv_taps == 9) a_row += (tap / 3 - 1) * (G.conv_w + 2) + (tap % 3 - 1);
+          const int c0 = (kb - tap * G.conv_cin_blocks) * kBK;
+          const int ky = G.conv_taps == 9 ? tap / 3 : 1, kx = G.conv_taps == 9 ? tap % 3 : 1;
+          const int sft = G.conv_stride - 1;
+          tma_load_3d_2cta(sa, &G.tmA, &full_bar[stage], c0, G.conv_stride * pt.x0 + kx + sft,
+                           G.conv_stride * pt.y0 + ky + sft);
+        } else {
+          tma_load_2d_2cta(sa, &G.tmA, &full_bar[stage], kb * kBK, my_m);
         }
-        tma_load_2d_2cta(sa, &G.tmA, &full_bar[stage], a_col, a_row);
         tma_load_2d_2cta(sa + kStageA, &G.tmB, &full_bar[stage], kb * kBK, my_n);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -262,8 +266,12 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       if (issuer && pair < p.total_tiles) {  // residual of the first chunk of the first tile
         const Tile2 tc = decode2(p, pair);
         mbar_arrive_expect_tx(&res_bar[0], kBox);
-        tma_load_2d(res_box, &p.g[tc.g].tmRes, &res_bar[0], tc.n0,
-                    out_row(p.g[tc.g], tc.m0 + rank * kRows));
+        if (p.g[tc.g].conv_w != 0) {
+          const PixTile q = pix_tile(p.g[tc.g], tc.m0 + rank * kRows);
+          tma_load_3d(res_box, &p.g[tc.g].tmRes, &res_bar[0], tc.n0, q.x0 + 1, q.y0 + 1);
+        } else {
+          tma_load_2d(res_box, &p.g[tc.g].tmRes, &res_bar[0], tc.n0, tc.m0 + rank * kRows);
+        }
       }
     }
     for (int t = pair; t < p.total_tiles; t += npairs) {
@@ -285,7 +293,12 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (issuer) {
-          tma_store_2d(&G.tmOut, ob, col, out_row(G, my_m));
+          if (G.conv_w != 0) {
+            const PixTile q = pix_tile(G, my_m);
+            tma_store_3d(&G.tmOut, ob, col, q.x0 + 1, q.y0 + 1);
+          } else {
+            tma_store_2d(&G.tmOut, ob, col, my_m);
+          }
           tma_store_commit();
         }
       };
@@ -370,8 +383,14 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
                 const Tile2 tn = decode2(p, nt);
                 const uint32_t nb = (cc + 1) & 1;
                 mbar_arrive_expect_tx(&res_bar[nb], kBox);
-                tma_load_2d(res_box + nb * kBox, &p.g[tn.g].tmRes, &res_bar[nb], tn.n0 + nc * 64,
-                            out_row(p.g[tn.g], tn.m0 + rank * kRows));
+                if (p.g[tn.g].conv_w != 0) {
+                  const PixTile q = pix_tile(p.g[tn.g], tn.m0 + rank * kRows);
+                  tma_load_3d(res_box + nb * kBox, &p.g[tn.g].tmRes, &res_bar[nb], tn.n0 + nc * 64,
+                              q.x0 + 1, q.y0 + 1);
+                } else {
+                  tma_load_2d(res_box + nb * kBox, &p.g[tn.g].tmRes, &res_bar[nb], tn.n0 + nc * 64,
+                              tn.m0 + rank * kRows);
+                }
               }
             }
             mbar_wait(&res_bar[cc & 1], (cc >> 1) & 1);
@@ -534,14 +553,21 @@ int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups
   return gemm2_dispatch(epi, p, tiles, rows, stream);
 }
 
-// 3x3 (taps = 9) or 1x1 (taps = 1) convolution, stride 1, zero padding, NHWC bf16 with a one-pixel
-// zero ring: in [(H+2)(W+2), Cin], out [(H+2)(W+2), Cout] (interior written, ring untouched),
-// weights [Cout, taps * Cin] (tap-major K), optional residual res[(H+2)(W+2), Cout] added after the
-// bias rounding (ResnetBlock2D: x + conv2(...)).  W % 128 == 0, Cin % 64 == 0, Cout % 128 == 0.
+// 3x3 (taps = 9) or 1x1 (taps = 1) convolution, stride 1 (zero padding 1) or stride 2 (diffusers
+// Downsample2D: pad right/bottom by one, no other padding), NHWC bf16 images with a one-pixel zero
+// ring: in [(Hin+2)(Win+2), Cin], out [(H+2)(W+2), Cout] (interior written, ring untouched), weights
+// [Cout, taps * Cin] (tap-major K), optional residual res (same geometry as out) added after the bias
+// rounding (ResnetBlock2D: x + conv2(...)).  H, W are the OUTPUT size; Hin = stride * H.
+// Needs: Cin % 64 == 0, Cout % 128 == 0, W a power of two >= 8 (or a multiple of 128), H % (128/bx) == 0.
 int conv_launch(const bf16* in, const bf16* weight, const bf16* bias, bf16* out, const bf16* res,
-                const bf16* ones, int H, int W, int Cin, int Cout, int taps, cudaStream_t stream) {
-  if (W % 128 != 0 || Cin % 64 != 0 || Cout % 128 != 0 || (taps != 9 && taps != 1)) {
-    set_error("conv_launch: need W % 128 == 0, Cin % 64 == 0, Cout % 128 == 0, taps in {1, 9}");
+                const bf16* ones, int H, int W, int Cin, int Cout, int taps, int stride,
+                cudaStream_t stream) {
+  const int bx = W >= 128 ? 128 : W;
+  const int by = 128 / bx;
+  if (Cin % 64 != 0 || Cout % 128 != 0 || (taps != 9 && taps != 1) || (stride != 1 && stride != 2) ||
+      W % bx != 0 || 128 % bx != 0 || H % by != 0 || (static_cast<long long>(H) * W) % 256 != 0) {
+    set_error("conv_launch: unsupported geometry (Cin % 64, Cout % 128, W = 2^k or multiple of 128, "
+              "H divisible by 128 / min(W, 128))");
     return -1;
   }
   Gemm2Params p;
@@ -554,15 +580,15 @@ int conv_launch(const bf16* in, const bf16* weight, const bf16* bias, bf16* out,
   p.num_kb = p.K / kBK;
   p.band = p.n_tiles;
   Gemm2Group& d = p.g[0];
-  const uint64_t prow = static_cast<uint64_t>(H + 2) * (W + 2);
-  int rc = make_tmap_2d(&d.tmA, in, prow, Cin, Cin, kRows);
+  const int Hin = stride * H, Win = stride * W;
+  int rc = make_tmap_3d(&d.tmA, in, Cin, Win + 2, Hin + 2, bx, by, stride);
   if (rc) return rc;
   rc = make_tmap_2d(&d.tmB, weight, Cout, p.K, p.K, p.bn / 2);
   if (rc) return rc;
-  rc = make_tmap_2d(&d.tmOut, out, prow, Cout, Cout, kRows);
+  rc = make_tmap_3d(&d.tmOut, out, Cout, W + 2, H + 2, bx, by, 1);
   if (rc) return rc;
   if (res) {
-    rc = make_tmap_2d(&d.tmRes, res, prow, Cout, Cout, kRows);
+    rc = make_tmap_3d(&d.tmRes, res, Cout, W + 2, H + 2, bx, by, 1);
     if (rc) return rc;
   }
   d.bias = bias;
@@ -572,6 +598,9 @@ int conv_launch(const bf16* in, const bf16* weight, const bf16* bias, bf16* out,
   d.conv_w = W;
   d.conv_taps = taps;
   d.conv_cin_blocks = Cin / kBK;
+  d.conv_bx = bx;
+  d.conv_by = by;
+  d.conv_stride = stride;
   return gemm2_dispatch(res ? EPI_GATE_RES : EPI_BIAS, p, d.m_pairs * p.n_tiles,
                         static_cast<double>(d.M), stream);
 }

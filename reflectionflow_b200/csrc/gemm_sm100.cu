@@ -407,6 +407,31 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 
 static long long* g_gemm_trace = nullptr;
 void dbg_set_gemm_trace(long long* p) { g_gemm_trace = p; }
+int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp,
+                 uint32_t box_x, uint32_t box_y, uint32_t stride) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return -3;
+  }
+  cuuint64_t gdim[3] = {C, Wp, Hp};
+  cuuint64_t gstride[2] = {C * 2, Wp * C * 2};
+  cuuint32_t box[3] = {64, box_x * stride, box_y * stride};
+  cuuint32_t estr[3] = {1, stride, stride};
+  if (box[1] > 256 || box[2] > 256) {
+    set_error("make_tmap_3d: box dimension exceeds 256");
+    return -1;
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed, CUresult=" + std::to_string(static_cast<int>(r)));
+    return -3;
+  }
+  return 0;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {

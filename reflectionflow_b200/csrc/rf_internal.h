@@ -42,6 +42,11 @@ struct ProfScope {
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols = 64);
 
+// 3-D bf16 NHWC image map {C, Wp, Hp} with 128-byte swizzle; box {64, box_x, box_y} elements of the
+// traversed (strided) lattice, i.e. the box spans box_x * stride pixels in x.
+int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp,
+                 uint32_t box_x, uint32_t box_y, uint32_t stride);
+
 // ---------------------------------------------------------------------------- GEMM
 enum GemmEpilogue {
   EPI_BIAS = 0,      // out = bf16(acc + bias)

@@ -22,7 +22,8 @@
 
 namespace rf {
 int conv_launch(const bf16* in, const bf16* weight, const bf16* bias, bf16* out, const bf16* res,
-                const bf16* ones, int H, int W, int Cin, int Cout, int taps, cudaStream_t stream);
+                const bf16* ones, int H, int W, int Cin, int Cout, int taps, int stride,
+                cudaStream_t stream);
 
 // ------------------------------------------------------------------ weight repack
 // torch conv weight [Cout, Cin, kh, kw] -> [Cout_pad, (kh*kw) * Cin_pad], tap-major K, zero padded
@@ -382,7 +383,7 @@ int group_norm(rf_vae* h, const bf16* x, bf16* out, int H, int W, const Norm& n,
 }
 int conv(rf_vae* h, const ConvW& c, const bf16* in, bf16* out, const bf16* res, int H, int W,
          cudaStream_t s) {
-  return rf::conv_launch(in, c.w, c.b, out, res, h->ones, H, W, c.cin_pad, c.cout_pad, c.taps, s);
+  return rf::conv_launch(in, c.w, c.b, out, res, h->ones, H, W, c.cin_pad, c.cout_pad, c.taps, 1, s);
 }
 
 int ensure_workspace(rf_vae* h, int H, int W) {  // H, W: output image size
@@ -568,10 +569,15 @@ int rf_vae_decode(rf_vae* h, const void* packed_latents, int height, int width, 
     rf::set_error("rf_vae_decode: null argument");
     return -1;
   }
-  if (height % 16 != 0 || width % 16 != 0 || (width / 8) % 128 != 0) {
-    rf::set_error("rf_vae_decode: need height % 16 == 0 and width % 1024 == 0 (128-pixel row tiles at "
-                  "the latent resolution)");
-    return -1;
+  {
+    const int lw = width / 8, lh = height / 8;
+    const int bx = lw >= 128 ? 128 : lw;
+    if (height % 16 != 0 || width % 16 != 0 || lw < 8 || lw % bx != 0 || 128 % bx != 0 ||
+        lh % (128 / bx) != 0 || (lh * lw) % 256 != 0) {
+      rf::set_error("rf_vae_decode: height, width must be multiples of 16 with width/8 a power of two "
+                    "(or a multiple of 128) and (height/8)*(width/8) a multiple of 256");
+      return -1;
+    }
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   RF_TRYV(ensure_workspace(h, height, width));

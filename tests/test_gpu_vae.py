@@ -26,11 +26,10 @@ def _models():
     return _CACHE["m"]
 
 
-@pytest.mark.parametrize("height", [64, 128])
-def test_decode_matches_oracle(height):
-    width = 1024
+@pytest.mark.parametrize("height,width", [(64, 1024), (128, 1024), (256, 256), (128, 512)])
+def test_decode_matches_oracle(height, width):
     ref, ours = _models()
-    g = torch.Generator().manual_seed(height)
+    g = torch.Generator().manual_seed(height * 7 + width)
     packed = torch.randn(1, (height // 16) * (width // 16), 64, generator=g).to(torch.bfloat16)
     img_pt = ours.decode_packed(packed, height, width, "pt")
     img_u8 = ours.decode_packed(packed, height, width, "u8")
