@@ -157,8 +157,9 @@ int rf_dit_denoise(rf_dit* h, void* latents_inout, const void* txt, const void* 
 typedef struct rf_vae rf_vae;
 int rf_vae_create(rf_vae** out);
 void rf_vae_destroy(rf_vae* h);
-/* diffusers AutoencoderKL state-dict keys of the DECODER ("decoder.conv_in.weight", ...,
- * torch conv layout [Cout, Cin, kh, kw]); src = device bf16. */
+/* diffusers AutoencoderKL state-dict keys ("decoder.conv_in.weight", "encoder.down_blocks.0...",
+ * torch conv layout [Cout, Cin, kh, kw]); src = device bf16.  decode needs the decoder.* keys,
+ * encode the encoder.* keys. */
 int rf_vae_load_weight(rf_vae* h, const char* key, const void* src, int64_t numel);
 int rf_vae_missing_weights(rf_vae* h);
 /* packed latents [(H/16)(W/16), 64] bf16 (one image) -> image.  Applies
@@ -167,6 +168,14 @@ int rf_vae_missing_weights(rf_vae* h);
  * (either may be NULL).  width % 1024 == 0, height % 16 == 0. */
 int rf_vae_decode(rf_vae* h, const void* packed_latents, int height, int width, float scaling_factor,
                   float shift_factor, uint8_t* out_u8_hwc, void* out_bf16_chw, void* stream);
+/* encode_images() of train_flux/flux/pipeline_tools.py:7-30 (Condition.encode, condition.py:96-132):
+ * image [H, W, 3] uint8 (or bf16 [3, H, W] already in [-1, 1]; exactly one non-NULL) ->
+ * VaeImageProcessor.preprocess -> encoder -> posterior sample mean + std * eps with CALLER-PROVIDED
+ * eps (bf16 [16, H/8, W/8]; NULL = posterior mode; the reference draws eps from the global RNG)
+ * -> (z - shift) * scaling -> packed tokens [(H/16)(W/16), 64] bf16. */
+int rf_vae_encode(rf_vae* h, const uint8_t* image_u8_hwc, const void* image_bf16_chw, int height,
+                  int width, const void* eps_bf16_chw, float scaling_factor, float shift_factor,
+                  void* packed_out, void* stream);
 
 /* Per-kernel timing of everything launched between start and stop (CUDA events on the launching
  * stream around each launch; graph-captured launches are skipped).  rf_profile_stop synchronises

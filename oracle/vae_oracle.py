@@ -222,3 +222,23 @@ def decode_latents(vae: AutoencoderKL, packed_latents, height: int, width: int):
     z = unpack_latents(packed_latents, height, width)
     z = (z / SCALING_FACTOR) + SHIFT_FACTOR
     return vae.decode(z)
+
+
+def encode_images(vae: AutoencoderKL, image_u8_hwc: torch.Tensor, eps: torch.Tensor = None,
+                  dtype=torch.bfloat16):
+    """train_flux/flux/pipeline_tools.py:7-30 with the posterior noise made explicit:
+    VaeImageProcessor.preprocess (uint8 -> [0,1] fp32 -> 2x-1) -> .to(dtype) -> vae.encode ->
+    DiagonalGaussianDistribution.sample (mean + std * eps; eps=None -> mode) -> (z - shift) * scale
+    -> FluxPipeline._pack_latents.  image_u8_hwc: [H, W, 3] uint8."""
+    from .flux_oracle import pack_latents
+    x = image_u8_hwc.permute(2, 0, 1)[None].float() / 255.0
+    x = (2.0 * x - 1.0).to(dtype)
+    mean, logvar = vae.encode_moments(x)
+    if eps is None:
+        z = mean
+    else:
+        std = torch.exp(0.5 * logvar)
+        z = mean + std * eps.to(dtype)[None]
+    z = (z - SHIFT_FACTOR) * SCALING_FACTOR
+    b, c, h, w = z.shape
+    return pack_latents(z, b, c, h, w)

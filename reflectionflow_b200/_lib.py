@@ -55,6 +55,8 @@ def _declare(lib):
         lib.rf_vae_missing_weights.argtypes = [vp]
         lib.rf_vae_decode.restype = ci
         lib.rf_vae_decode.argtypes = [vp, vp, ci, ci, cf, cf, vp, vp, vp]
+        lib.rf_vae_encode.restype = ci
+        lib.rf_vae_encode.argtypes = [vp, vp, vp, ci, ci, vp, cf, cf, vp, vp]
     if hasattr(lib, "rf_dit_create"):
         lib.rf_dit_create.restype = ci
         lib.rf_dit_create.argtypes = [vp, POINTER(vp)]

@@ -257,6 +257,50 @@ __global__ void postprocess_kernel(const bf16* __restrict__ x, int H, int W, int
   }
 }
 
+// image -> padded NHWC [(H+2)(W+2), 64] (3 real channels): VaeImageProcessor.preprocess
+// (uint8 / 255 -> 2x - 1 in fp32, then .to(bf16)); `chw` (bf16 [3,H,W] already in [-1,1]) is the
+// alternative input
+__global__ void image_to_nhwc_kernel(const uint8_t* __restrict__ u8, const bf16* __restrict__ chw,
+                                     bf16* __restrict__ out, int H, int W) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(H) * W) return;
+  const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<long long>(y) * W);
+  bf16* px = out + (static_cast<size_t>(y + 1) * (W + 2) + x + 1) * 64;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (u8) {
+      const float v = static_cast<float>(u8[i * 3 + c]) / 255.0f;
+      px[c] = __float2bfloat16_rn(2.0f * v - 1.0f);
+    } else {
+      px[c] = chw[(static_cast<size_t>(c) * H + y) * W + x];
+    }
+  }
+}
+// moments (padded NHWC, channels 0..15 mean, 16..31 logvar) -> posterior sample -> (z - shift) * scale
+// -> FluxPipeline._pack_latents layout [(h/2)(w/2), 64].  eps: bf16 [16, h, w] or NULL (mode).
+// Rounding points of diffusers DiagonalGaussianDistribution + pipeline_tools.py:10-14 in bf16.
+__global__ void sample_pack_kernel(const bf16* __restrict__ mom, int C, const bf16* __restrict__ eps,
+                                   bf16* __restrict__ packed, int h, int w, float scaling, float shift) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // pixel * 16 + c
+  if (idx >= h * w * 16) return;
+  const int c = idx & 15, pix = idx >> 4;
+  const int y = pix / w, x = pix - y * w;
+  const bf16* px = mom + (static_cast<size_t>(y + 1) * (w + 2) + x + 1) * C;
+  const float mean = __bfloat162float(px[c]);
+  float z = mean;
+  if (eps) {
+    float lv = fminf(fmaxf(__bfloat162float(px[16 + c]), -30.0f), 20.0f);
+    const float sd = bf16_round(expf(bf16_round(0.5f * lv)));
+    const float e = __bfloat162float(eps[(static_cast<size_t>(c) * h + y) * w + x]);
+    z = bf16_round(mean + bf16_round(sd * e));
+  }
+  z = bf16_round(z - shift);
+  z = bf16_round(z * scaling);
+  const int tok = (y >> 1) * (w >> 1) + (x >> 1);
+  const int ch = c * 4 + (y & 1) * 2 + (x & 1);
+  packed[static_cast<size_t>(tok) * 64 + ch] = __float2bfloat16_rn(z);
+}
+
 }  // namespace rf
 
 using rf::bf16;
@@ -286,15 +330,26 @@ struct LinearW {
 }  // namespace
 
 extern "C" int rf_vae_missing_weights(struct rf_vae* h);
+static int vae_missing(struct rf_vae* h, const char* prefix);
+struct MidBlock {
+  Resnet res[2];
+  Norm attn_gn;
+  LinearW attn_qkv, attn_out;  // to_q|to_k|to_v stacked [1536, 512]
+};
+
 struct rf_vae {
   std::vector<void*> allocs;
   ConvW conv_in, conv_out;
   Norm norm_out;
-  Resnet mid[2];
-  Norm attn_gn;
-  LinearW attn_qkv, attn_out;  // to_q|to_k|to_v stacked [1536, 512]
+  MidBlock mid;
   Resnet up[4][3];
   ConvW upconv[3];
+  // encoder
+  ConvW e_conv_in, e_conv_out;
+  Norm e_norm_out;
+  MidBlock e_mid;
+  Resnet down[4][2];
+  ConvW downconv[3];
   struct Slot { int kind; void* obj; int part; };  // kind 0 conv w, 1 conv b, 2 norm g, 3 norm b, 4 lin w, 5 lin b
   std::unordered_map<std::string, Slot> slots;
   bf16* ones = nullptr;
@@ -350,6 +405,26 @@ int make_resnet(rf_vae* h, Resnet& r, const std::string& key, int cin, int cout)
   RF_TRYV(make_conv(h, r.c2, key + ".conv2", cout, cout, 9));
   r.has_sc = cin != cout;
   if (r.has_sc) RF_TRYV(make_conv(h, r.sc, key + ".conv_shortcut", cin, cout, 1));
+  return 0;
+}
+
+int make_mid(rf_vae* h, MidBlock& m, const std::string& key) {
+  RF_TRYV(make_resnet(h, m.res[0], key + ".resnets.0", 512, 512));
+  RF_TRYV(make_resnet(h, m.res[1], key + ".resnets.1", 512, 512));
+  RF_TRYV(make_norm(h, m.attn_gn, key + ".attentions.0.group_norm", 512));
+  void* p;
+  RF_TRYV(valloc(h, &p, static_cast<size_t>(1536) * 512 * 2)); m.attn_qkv.w = static_cast<bf16*>(p);
+  RF_TRYV(valloc(h, &p, 1536 * 2)); m.attn_qkv.b = static_cast<bf16*>(p);
+  RF_TRYV(valloc(h, &p, static_cast<size_t>(512) * 512 * 2)); m.attn_out.w = static_cast<bf16*>(p);
+  RF_TRYV(valloc(h, &p, 512 * 2)); m.attn_out.b = static_cast<bf16*>(p);
+  const char* nm[3] = {"to_q", "to_k", "to_v"};
+  for (int j = 0; j < 3; ++j) {
+    const std::string k = key + ".attentions.0." + nm[j];
+    h->slots[k + ".weight"] = {4, &m.attn_qkv, j};
+    h->slots[k + ".bias"] = {5, &m.attn_qkv, j};
+  }
+  h->slots[key + ".attentions.0.to_out.0.weight"] = {4, &m.attn_out, 3};
+  h->slots[key + ".attentions.0.to_out.0.bias"] = {5, &m.attn_out, 3};
   return 0;
 }
 
@@ -440,6 +515,55 @@ int resnet(rf_vae* h, const Resnet& r, int x, int out, int t1, int t2, int H, in
   return conv(h, r.c2, h->buf[t1], h->buf[out], shortcut, H, W, s);
 }
 
+// UNetMidBlock2D: resnet, self-attention over H*W tokens (1 head x 512), resnet.  buf[x] -> buf[x].
+int mid_block(rf_vae* h, const MidBlock& m, int& x, int& y, int t1, int t2, int H, int W, cudaStream_t s) {
+  RF_TRYV(resnet(h, m.res[0], x, y, t1, t2, H, W, s));
+  std::swap(x, y);
+  const int ntok = H * W;
+  RF_TRYV(group_norm(h, h->buf[x], h->tok, H, W, m.attn_gn, 0, 1, 0, s));  // compact tokens
+  rf::repad_kernel<<<grid_for(static_cast<long long>(ntok) * 64), 256, 0, s>>>(h->buf[x], h->tokx, H, W, 512,
+                                                                              1, 0);
+  RF_CHECK_CUDA(cudaGetLastError());
+  rf::count_launch();
+  rf::GemmGroupArgs g;
+  memset(&g, 0, sizeof(g));  // q | k | v
+  g.A = h->tok; g.lda = 512; g.M = ntok; g.W = m.attn_qkv.w; g.bias = m.attn_qkv.b;
+  g.out = h->qkv; g.ldo = 1536;
+  RF_TRYV(rf::gemm_launch(rf::EPI_BIAS, 1536, 512, 1, &g, s));
+  // the GEMM's W operand is [N, K] with pitch K: stage K compactly (ay is free until the out-proj)
+  RF_CHECK_CUDA(cudaMemcpy2DAsync(h->ay, 512 * 2, h->qkv + 512, 1536 * 2, 512 * 2, ntok,
+                                  cudaMemcpyDeviceToDevice, s));
+  memset(&g, 0, sizeof(g));  // S = Q K^T
+  g.A = h->qkv; g.lda = 1536; g.M = ntok; g.W = h->ay; g.out = h->S; g.ldo = ntok;
+  RF_TRYV(rf::gemm_launch(rf::EPI_BIAS, ntok, 512, 1, &g, s));
+  {
+    rf::ProfScope prof("vae_softmax", 0, 4.0 * ntok * ntok, s);
+    rf::softmax_rows_kernel<<<ntok, 256, 0, s>>>(h->S, ntok, 1.0f / sqrtf(512.0f));
+  }
+  RF_CHECK_CUDA(cudaGetLastError());
+  rf::count_launch();
+  dim3 tg(512 / 32, ntok / 32), tb(32, 8);
+  rf::transpose_kernel<<<tg, tb, 0, s>>>(h->qkv + 1024, 1536, h->vt, ntok, 512);  // V^T [512, ntok]
+  RF_CHECK_CUDA(cudaGetLastError());
+  rf::count_launch();
+  memset(&g, 0, sizeof(g));  // O = P V
+  g.A = h->S; g.lda = ntok; g.M = ntok; g.W = h->vt; g.out = h->ao; g.ldo = 512;
+  RF_TRYV(rf::gemm_launch(rf::EPI_BIAS, 512, ntok, 1, &g, s));
+  memset(&g, 0, sizeof(g));  // y = x + to_out(O)
+  g.A = h->ao; g.lda = 512; g.M = ntok; g.W = m.attn_out.w; g.bias = m.attn_out.b;
+  g.out = h->ay; g.ldo = 512; g.res = h->tokx; g.ldr = 512; g.gate = h->ones;
+  RF_TRYV(rf::gemm_launch(rf::EPI_GATE_RES, 512, 512, 1, &g, s));
+  RF_TRYV(prep(h, y, H, W, 512, s));
+  rf::repad_kernel<<<grid_for(static_cast<long long>(ntok) * 64), 256, 0, s>>>(h->ay, h->buf[y], H, W, 512,
+                                                                              0, 1);
+  RF_CHECK_CUDA(cudaGetLastError());
+  rf::count_launch();
+  std::swap(x, y);
+  RF_TRYV(resnet(h, m.res[1], x, y, t1, t2, H, W, s));
+  std::swap(x, y);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -458,24 +582,7 @@ int rf_vae_create(rf_vae** out) {
   int rc = 0;
   auto chk = [&](int r) { if (r && !rc) rc = r; };
   chk(make_conv(h, h->conv_in, "decoder.conv_in", 16, 512, 9));
-  chk(make_resnet(h, h->mid[0], "decoder.mid_block.resnets.0", 512, 512));
-  chk(make_resnet(h, h->mid[1], "decoder.mid_block.resnets.1", 512, 512));
-  chk(make_norm(h, h->attn_gn, "decoder.mid_block.attentions.0.group_norm", 512));
-  {
-    void* p;
-    chk(valloc(h, &p, static_cast<size_t>(1536) * 512 * 2)); h->attn_qkv.w = static_cast<bf16*>(p);
-    chk(valloc(h, &p, 1536 * 2)); h->attn_qkv.b = static_cast<bf16*>(p);
-    chk(valloc(h, &p, static_cast<size_t>(512) * 512 * 2)); h->attn_out.w = static_cast<bf16*>(p);
-    chk(valloc(h, &p, 512 * 2)); h->attn_out.b = static_cast<bf16*>(p);
-    const char* nm[3] = {"to_q", "to_k", "to_v"};
-    for (int j = 0; j < 3; ++j) {
-      const std::string k = std::string("decoder.mid_block.attentions.0.") + nm[j];
-      h->slots[k + ".weight"] = {4, &h->attn_qkv, j};
-      h->slots[k + ".bias"] = {5, &h->attn_qkv, j};
-    }
-    h->slots["decoder.mid_block.attentions.0.to_out.0.weight"] = {4, &h->attn_out, 3};
-    h->slots["decoder.mid_block.attentions.0.to_out.0.bias"] = {5, &h->attn_out, 3};
-  }
+  chk(make_mid(h, h->mid, "decoder.mid_block"));
   const int chans[4] = {512, 512, 256, 128};
   int prev = 512;
   for (int i = 0; i < 4; ++i) {
@@ -490,6 +597,25 @@ int rf_vae_create(rf_vae** out) {
   }
   chk(make_norm(h, h->norm_out, "decoder.conv_norm_out", 128));
   chk(make_conv(h, h->conv_out, "decoder.conv_out", 128, 3, 9));
+  // ---- encoder (diffusers Encoder: conv_in, 4 down blocks x 2 resnets, mid block, norm, conv_out)
+  chk(make_conv(h, h->e_conv_in, "encoder.conv_in", 3, 128, 9));
+  {
+    const int ech[4] = {128, 256, 512, 512};
+    int ep = 128;
+    for (int i = 0; i < 4; ++i) {
+      for (int j = 0; j < 2; ++j)
+        chk(make_resnet(h, h->down[i][j],
+                        "encoder.down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j),
+                        j == 0 ? ep : ech[i], ech[i]));
+      if (i < 3)
+        chk(make_conv(h, h->downconv[i],
+                      "encoder.down_blocks." + std::to_string(i) + ".downsamplers.0.conv", ech[i], ech[i], 9));
+      ep = ech[i];
+    }
+  }
+  chk(make_mid(h, h->e_mid, "encoder.mid_block"));
+  chk(make_norm(h, h->e_norm_out, "encoder.conv_norm_out", 512));
+  chk(make_conv(h, h->e_conv_out, "encoder.conv_out", 512, 32, 9));
   {
     void* p;
     chk(valloc(h, &p, 512 * 2));
@@ -581,7 +707,7 @@ int rf_vae_decode(rf_vae* h, const void* packed_latents, int height, int width, 
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   RF_TRYV(ensure_workspace(h, height, width));
-  if (rf_vae_missing_weights(h) != 0) return -4;
+  if (vae_missing(h, "decoder.") != 0) return -4;
   int H = height / 8, W = width / 8;
   int x = 0, y = 1;
   const int t1 = 2, t2 = 3;
@@ -594,53 +720,7 @@ int rf_vae_decode(rf_vae* h, const void* packed_latents, int height, int width, 
   RF_TRYV(prep(h, y, H, W, 512, s));
   RF_TRYV(conv(h, h->conv_in, h->buf[x], h->buf[y], nullptr, H, W, s));
   std::swap(x, y);
-  // ---- mid block: resnet, self-attention over H*W tokens (1 head x 512), resnet
-  RF_TRYV(resnet(h, h->mid[0], x, y, t1, t2, H, W, s));
-  std::swap(x, y);
-  {
-    const int ntok = H * W;
-    RF_TRYV(group_norm(h, h->buf[x], h->tok, H, W, h->attn_gn, 0, 1, 0, s));  // compact tokens
-    rf::repad_kernel<<<grid_for(static_cast<long long>(ntok) * 64), 256, 0, s>>>(h->buf[x], h->tokx, H, W,
-                                                                                512, 1, 0);
-    RF_CHECK_CUDA(cudaGetLastError());
-    rf::count_launch();
-    rf::GemmGroupArgs g;
-    memset(&g, 0, sizeof(g));  // q | k | v
-    g.A = h->tok; g.lda = 512; g.M = ntok; g.W = h->attn_qkv.w; g.bias = h->attn_qkv.b;
-    g.out = h->qkv; g.ldo = 1536;
-    RF_TRYV(rf::gemm_launch(rf::EPI_BIAS, 1536, 512, 1, &g, s));
-    // the GEMM's W operand is [N, K] with pitch K: stage K compactly (ay is free until the out-proj)
-    RF_CHECK_CUDA(cudaMemcpy2DAsync(h->ay, 512 * 2, h->qkv + 512, 1536 * 2, 512 * 2, ntok,
-                                    cudaMemcpyDeviceToDevice, s));
-    memset(&g, 0, sizeof(g));  // S = Q K^T
-    g.A = h->qkv; g.lda = 1536; g.M = ntok; g.W = h->ay; g.out = h->S; g.ldo = ntok;
-    RF_TRYV(rf::gemm_launch(rf::EPI_BIAS, ntok, 512, 1, &g, s));
-    {
-      rf::ProfScope prof("vae_softmax", 0, 4.0 * ntok * ntok, s);
-      rf::softmax_rows_kernel<<<ntok, 256, 0, s>>>(h->S, ntok, 1.0f / sqrtf(512.0f));
-    }
-    RF_CHECK_CUDA(cudaGetLastError());
-    rf::count_launch();
-    dim3 tg(512 / 32, ntok / 32), tb(32, 8);
-    rf::transpose_kernel<<<tg, tb, 0, s>>>(h->qkv + 1024, 1536, h->vt, ntok, 512);  // V^T [512, ntok]
-    RF_CHECK_CUDA(cudaGetLastError());
-    rf::count_launch();
-    memset(&g, 0, sizeof(g));  // O = P V
-    g.A = h->S; g.lda = ntok; g.M = ntok; g.W = h->vt; g.out = h->ao; g.ldo = 512;
-    RF_TRYV(rf::gemm_launch(rf::EPI_BIAS, 512, ntok, 1, &g, s));
-    memset(&g, 0, sizeof(g));  // y = x + to_out(O)
-    g.A = h->ao; g.lda = 512; g.M = ntok; g.W = h->attn_out.w; g.bias = h->attn_out.b;
-    g.out = h->ay; g.ldo = 512; g.res = h->tokx; g.ldr = 512; g.gate = h->ones;
-    RF_TRYV(rf::gemm_launch(rf::EPI_GATE_RES, 512, 512, 1, &g, s));
-    RF_TRYV(prep(h, y, H, W, 512, s));
-    rf::repad_kernel<<<grid_for(static_cast<long long>(ntok) * 64), 256, 0, s>>>(h->ay, h->buf[y], H, W,
-                                                                                512, 0, 1);
-    RF_CHECK_CUDA(cudaGetLastError());
-    rf::count_launch();
-    std::swap(x, y);
-  }
-  RF_TRYV(resnet(h, h->mid[1], x, y, t1, t2, H, W, s));
-  std::swap(x, y);
+  RF_TRYV(mid_block(h, h->mid, x, y, t1, t2, H, W, s));  // result back in buf[x]
   // ---- up blocks: 3 resnets each, nearest 2x + conv between them
   for (int i = 0; i < 4; ++i) {
     for (int j = 0; j < 3; ++j) {
@@ -675,11 +755,79 @@ int rf_vae_decode(rf_vae* h, const void* packed_latents, int height, int width, 
   return 0;
 }
 
-int rf_vae_missing_weights(rf_vae* h) {
+int rf_vae_missing_weights(rf_vae* h) { return vae_missing(h, ""); }
+
+/* image [H, W, 3] uint8 (or bf16 CHW in [-1, 1]) -> packed condition latents [(H/16)(W/16), 64]:
+ * preprocess, encoder, posterior sample with caller-provided eps (NULL = mode), (z - shift) * scale,
+ * pack.  Replaces encode_images() of train_flux/flux/pipeline_tools.py:7-30. */
+int rf_vae_encode(rf_vae* h, const uint8_t* image_u8_hwc, const void* image_bf16_chw, int height,
+                  int width, const void* eps_bf16_chw, float scaling_factor, float shift_factor,
+                  void* packed_out, void* stream) {
+  if (!h || (!image_u8_hwc && !image_bf16_chw) || !packed_out) {
+    rf::set_error("rf_vae_encode: null argument");
+    return -1;
+  }
+  {
+    const int lw = width / 8, lh = height / 8;
+    const int bx = lw >= 128 ? 128 : lw;
+    if (height % 16 != 0 || width % 16 != 0 || lw < 8 || lw % bx != 0 || 128 % bx != 0 ||
+        lh % (128 / bx) != 0 || (lh * lw) % 256 != 0) {
+      rf::set_error("rf_vae_encode: height, width must be multiples of 16 with width/8 a power of two "
+                    "(or a multiple of 128) and (height/8)*(width/8) a multiple of 256");
+      return -1;
+    }
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RF_TRYV(ensure_workspace(h, height, width));
+  if (vae_missing(h, "encoder.") != 0) return -4;
+  int H = height, W = width;
+  int x = 0, y = 1;
+  const int t1 = 2, t2 = 3;
+  RF_TRYV(prep(h, x, H, W, 64, s));
+  rf::image_to_nhwc_kernel<<<static_cast<int>((static_cast<long long>(H) * W + 255) / 256), 256, 0, s>>>(
+      image_u8_hwc, static_cast<const bf16*>(image_bf16_chw), h->buf[x], H, W);
+  RF_CHECK_CUDA(cudaGetLastError());
+  rf::count_launch();
+  RF_TRYV(prep(h, y, H, W, 128, s));
+  RF_TRYV(conv(h, h->e_conv_in, h->buf[x], h->buf[y], nullptr, H, W, s));
+  std::swap(x, y);
+  for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < 2; ++j) {
+      RF_TRYV(resnet(h, h->down[i][j], x, y, t1, t2, H, W, s));
+      std::swap(x, y);
+    }
+    if (i < 3) {  // Downsample2D: pad (0,1,0,1) + conv3x3 stride 2 == strided taps over the zero ring
+      const ConvW& c = h->downconv[i];
+      H /= 2;
+      W /= 2;
+      RF_TRYV(prep(h, y, H, W, c.cout_pad, s));
+      RF_TRYV(rf::conv_launch(h->buf[x], c.w, c.b, h->buf[y], nullptr, h->ones, H, W, c.cin_pad,
+                              c.cout_pad, 9, 2, s));
+      std::swap(x, y);
+    }
+  }
+  RF_TRYV(mid_block(h, h->e_mid, x, y, t1, t2, H, W, s));
+  RF_TRYV(prep(h, t1, H, W, 512, s));
+  RF_TRYV(group_norm(h, h->buf[x], h->buf[t1], H, W, h->e_norm_out, 1, 1, 1, s));
+  RF_TRYV(prep(h, y, H, W, 128, s));
+  RF_TRYV(conv(h, h->e_conv_out, h->buf[t1], h->buf[y], nullptr, H, W, s));  // 32 moments (of 128)
+  rf::sample_pack_kernel<<<(H * W * 16 + 255) / 256, 256, 0, s>>>(
+      h->buf[y], 128, static_cast<const bf16*>(eps_bf16_chw), static_cast<bf16*>(packed_out), H, W,
+      scaling_factor, shift_factor);
+  RF_CHECK_CUDA(cudaGetLastError());
+  rf::count_launch();
+  return 0;
+}
+
+}  // extern "C"
+
+static int vae_missing(rf_vae* h, const char* prefix) {
   if (!h) return -1;
   int missing = 0;
   std::string names;
+  const size_t pl = strlen(prefix);
   for (auto& kv : h->slots) {
+    if (kv.first.compare(0, pl, prefix) != 0) continue;
     bool ok = true;
     const rf_vae::Slot& sl = kv.second;
     if (sl.kind == 0) ok = static_cast<ConvW*>(sl.obj)->w_loaded;
@@ -696,5 +844,3 @@ int rf_vae_missing_weights(rf_vae* h) {
   if (missing) rf::set_error("missing VAE weights: " + names);
   return missing;
 }
-
-}  // extern "C"

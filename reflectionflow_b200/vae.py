@@ -45,10 +45,10 @@ class B200AutoencoderKL:
             pass
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
-        """diffusers AutoencoderKL keys; only `decoder.*` is consumed (the encoder is not native yet)."""
+        """diffusers AutoencoderKL keys (`decoder.*` and `encoder.*`)."""
         with torch.cuda.device(self.device):
             for k, v in sd.items():
-                if not k.startswith("decoder."):
+                if not (k.startswith("decoder.") or k.startswith("encoder.")):
                     continue
                 t = v.detach().to(self.device, torch.bfloat16).contiguous()
                 L.check(self._lib.rf_vae_load_weight(self._h, k.encode(), L.ptr(t), t.numel()),
@@ -97,6 +97,23 @@ class B200AutoencoderKL:
                 prev = c
             norm("decoder.conv_norm_out", 128)
             conv("decoder.conv_out", 3, 128, 3)
+            conv("encoder.conv_in", 128, 3, 3)
+            prev = 128
+            for i, c in enumerate((128, 256, 512, 512)):
+                for j in range(2):
+                    resnet(f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else c, c)
+                if i < 3:
+                    conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", c, c, 3)
+                prev = c
+            resnet("encoder.mid_block.resnets.0", 512, 512)
+            resnet("encoder.mid_block.resnets.1", 512, 512)
+            a = "encoder.mid_block.attentions.0."
+            norm(a + "group_norm", 512)
+            for n in ("to_q", "to_k", "to_v", "to_out.0"):
+                put(a + n + ".weight", torch.randn(512, 512, generator=g, device=self.device) / 512 ** 0.5)
+                put(a + n + ".bias", 0.05 * torch.randn(512, generator=g, device=self.device))
+            norm("encoder.conv_norm_out", 512)
+            conv("encoder.conv_out", 32, 512, 3)
             if self._lib.rf_vae_missing_weights(self._h) != 0:
                 L.check(-4, "init_synthetic_weights")
         return self
@@ -116,6 +133,40 @@ class B200AutoencoderKL:
                     ctypes.c_float(self.config.shift_factor), L.ptr(u8[b]) if u8 is not None else None,
                     L.ptr(pt[b]) if pt is not None else None, L.cur_stream()), "rf_vae_decode")
         return u8 if output == "u8" else pt
+
+
+    @torch.no_grad()
+    def _encode(self, image_u8=None, image_pt=None, eps: Optional[torch.Tensor] = None):
+        if image_u8 is not None:
+            img = image_u8.detach().to(self.device, torch.uint8).contiguous()
+            B, H, W = img.shape[0], img.shape[1], img.shape[2]
+        else:
+            img = image_pt.detach().to(self.device, torch.bfloat16).contiguous()
+            B, H, W = img.shape[0], img.shape[2], img.shape[3]
+        out = torch.empty((B, (H // 16) * (W // 16), 64), dtype=torch.bfloat16, device=self.device)
+        if eps is not None:
+            eps = eps.detach().to(self.device, torch.bfloat16).contiguous()
+            if eps.dim() == 3:
+                eps = eps[None].expand(B, -1, -1, -1).contiguous()
+        with torch.cuda.device(self.device):
+            for b in range(B):
+                L.check(self._lib.rf_vae_encode(
+                    self._h, L.ptr(img[b]) if image_u8 is not None else None,
+                    L.ptr(img[b]) if image_u8 is None else None, H, W,
+                    L.ptr(eps[b]) if eps is not None else None,
+                    ctypes.c_float(self.config.scaling_factor), ctypes.c_float(self.config.shift_factor),
+                    L.ptr(out[b]), L.cur_stream()), "rf_vae_encode")
+        return out
+
+    def encode_packed(self, image_u8: torch.Tensor, eps: Optional[torch.Tensor] = None):
+        """uint8 [B, H, W, 3] -> packed condition tokens [B, (H/16)(W/16), 64] (encode_images of
+        train_flux/flux/pipeline_tools.py:7-30).  eps: bf16 [16, H/8, W/8] posterior noise (the
+        reference samples it from the global RNG); None = posterior mode."""
+        return self._encode(image_u8=image_u8, eps=eps)
+
+    def encode_packed_pt(self, image_pt: torch.Tensor, eps: Optional[torch.Tensor] = None):
+        """bf16 [B, 3, H, W] in [-1, 1] (already preprocessed) -> packed tokens."""
+        return self._encode(image_pt=image_pt, eps=eps)
 
 
 def to_pil(u8: torch.Tensor) -> List:

@@ -54,6 +54,29 @@ def test_decode_matches_oracle(height, width):
     assert (du <= 2).float().mean() > 0.99
 
 
+@pytest.mark.parametrize("height,width,use_eps", [(256, 256, True), (128, 512, False), (512, 512, True)])
+def test_encode_matches_oracle(height, width, use_eps):
+    """encode_images(): preprocess -> encoder (stride-2 convs, mid attention) -> posterior sample with
+    explicit eps -> shift/scale -> pack"""
+    ref, ours = _models()
+    g = torch.Generator().manual_seed(height + 3 * width)
+    img = torch.randint(0, 256, (height, width, 3), generator=g, dtype=torch.uint8)
+    eps = torch.randn(16, height // 8, width // 8, generator=g).to(torch.bfloat16) if use_eps else None
+    got = ours.encode_packed(img[None], eps)
+    torch.cuda.synchronize()
+    want = vo.encode_images(ref, img, eps)
+    want32 = vo.encode_images(ref.float(), img, eps, dtype=torch.float32)
+    ref.to(torch.bfloat16)
+    d = (got.cpu().float() - want.float()).abs()
+    e_ref = (want.float() - want32).abs()
+    e_ours = (got.cpu().float() - want32).abs()
+    print(f"[vae enc {height}x{width} eps={use_eps}] |ours-ref_bf16| mean {d.mean():.4g} max {d.max():.4g} ; "
+          f"|ref-fp32| mean {e_ref.mean():.4g} ; |ours-fp32| mean {e_ours.mean():.4g} ; absmax {want.float().abs().max():.3g}")
+    assert got.shape == want.shape and torch.isfinite(got.float()).all()
+    assert e_ours.mean() <= 1.5 * e_ref.mean() + 2e-3
+    assert d.mean() <= 3.0 * e_ref.mean() + 2e-3
+
+
 def test_postprocess_is_bit_exact_on_given_image():
     """the uint8 conversion itself (x/2+0.5 in bf16, clamp, *255, round-half-even) is exact: feed the
     oracle's own pre-quantisation image through the same formula"""
