@@ -85,6 +85,14 @@ int rf_op_timestep_embed(const void* t, float pre_scale, void* out, int batch, v
 int rf_op_euler_step(void* x, const void* v, const float* sigmas, const int* step, int n,
                      void* stream);
 
+/* Pillow-compatible BICUBIC resize of a uint8 HWC image (Image.resize default filter): the
+ * parent -> condition resize of tts/tts_reflectionflow.py:276-277.  Integer resampling tables
+ * (bounds [out,2] = (first, count), coef [out, ksize], 22 fractional bits) come from the host
+ * (reflectionflow_b200/resize.py::precompute_coeffs); tmp = uint8 [H, out_w, 3] scratch. */
+int rf_op_resize_u8(const uint8_t* in_hwc, int H, int W, uint8_t* tmp, uint8_t* out_hwc, int out_h,
+                    int out_w, const int* bounds_x, const int* coef_x, int ksize_x, const int* bounds_y,
+                    const int* coef_y, int ksize_y, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Model level: the FLUX DiT forward and the denoise loop.
  * ---------------------------------------------------------------------------------------- */

@@ -42,6 +42,8 @@ def _declare(lib):
     lib.rf_op_timestep_embed.argtypes = [vp, cf, vp, ci, vp]
     lib.rf_op_euler_step.restype = ci
     lib.rf_op_euler_step.argtypes = [vp, vp, vp, vp, ci, vp]
+    lib.rf_op_resize_u8.restype = ci
+    lib.rf_op_resize_u8.argtypes = [vp, ci, ci, vp, vp, ci, ci, vp, vp, ci, vp, vp, ci, vp]
     lib.rf_dbg_force_gemm_v1.restype = None
     lib.rf_dbg_force_gemm_v1.argtypes = [ci]
     if hasattr(lib, "rf_vae_create"):

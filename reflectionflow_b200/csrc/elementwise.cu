@@ -341,4 +341,55 @@ int copy_rows_launch(const bf16* src, int lds, bf16* dst, int ldd, int rows, int
   return 0;
 }
 
+// ------------------------------------------------------------------------- PIL-compatible resize
+// Pillow ImagingResample, uint8: out = clip8((2^21 + sum_k pix_k * coeff_k) >> 22), horizontal pass
+// into a uint8 intermediate, then vertical pass (tables from reflectionflow_b200/resize.py).
+__global__ void resize_h_kernel(const uint8_t* __restrict__ in, int H, int W, uint8_t* __restrict__ out,
+                                int OW, const int* __restrict__ bounds, const int* __restrict__ coef,
+                                int ksize) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(H) * OW) return;
+  const int y = static_cast<int>(i / OW), xx = static_cast<int>(i - static_cast<long long>(y) * OW);
+  const int x0 = bounds[2 * xx], n = bounds[2 * xx + 1];
+  int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+  const uint8_t* row = in + (static_cast<size_t>(y) * W + x0) * 3;
+  for (int k = 0; k < n; ++k) {
+    const int c = coef[xx * ksize + k];
+    a0 += row[3 * k] * c; a1 += row[3 * k + 1] * c; a2 += row[3 * k + 2] * c;
+  }
+  uint8_t* o = out + i * 3;
+  o[0] = static_cast<uint8_t>(min(max(a0 >> 22, 0), 255));
+  o[1] = static_cast<uint8_t>(min(max(a1 >> 22, 0), 255));
+  o[2] = static_cast<uint8_t>(min(max(a2 >> 22, 0), 255));
+}
+__global__ void resize_v_kernel(const uint8_t* __restrict__ in, int H, int W, uint8_t* __restrict__ out,
+                                int OH, const int* __restrict__ bounds, const int* __restrict__ coef,
+                                int ksize) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(OH) * W) return;
+  const int yy = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<long long>(yy) * W);
+  const int y0 = bounds[2 * yy], n = bounds[2 * yy + 1];
+  int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+  for (int k = 0; k < n; ++k) {
+    const int c = coef[yy * ksize + k];
+    const uint8_t* px = in + (static_cast<size_t>(y0 + k) * W + x) * 3;
+    a0 += px[0] * c; a1 += px[1] * c; a2 += px[2] * c;
+  }
+  uint8_t* o = out + i * 3;
+  o[0] = static_cast<uint8_t>(min(max(a0 >> 22, 0), 255));
+  o[1] = static_cast<uint8_t>(min(max(a1 >> 22, 0), 255));
+  o[2] = static_cast<uint8_t>(min(max(a2 >> 22, 0), 255));
+}
+int resize_u8_launch(const uint8_t* in, int H, int W, uint8_t* tmp, uint8_t* out, int OH, int OW,
+                     const int* bx, const int* kx, int ksx, const int* by, const int* ky, int ksy,
+                     cudaStream_t stream) {
+  const long long n1 = static_cast<long long>(H) * OW, n2 = static_cast<long long>(OH) * OW;
+  resize_h_kernel<<<static_cast<int>((n1 + 255) / 256), 256, 0, stream>>>(in, H, W, tmp, OW, bx, kx, ksx);
+  RF_CHECK_CUDA(cudaGetLastError());
+  resize_v_kernel<<<static_cast<int>((n2 + 255) / 256), 256, 0, stream>>>(tmp, H, OW, out, OH, by, ky, ksy);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
+  return 0;
+}
+
 }  // namespace rf

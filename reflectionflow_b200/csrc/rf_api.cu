@@ -39,6 +39,11 @@ ProfScope::~ProfScope() {
 }  // namespace rf
 
 using rf::bf16;
+namespace rf {
+int resize_u8_launch(const uint8_t* in, int H, int W, uint8_t* tmp, uint8_t* out, int OH, int OW,
+                     const int* bx, const int* kx, int ksx, const int* by, const int* ky, int ksy,
+                     cudaStream_t stream);
+}
 namespace rf { void dbg_set_attn_trace(long long* p); void dbg_set_gemm_trace(long long* p); void dbg_force_gemm_v1(bool on); }
 
 extern "C" {
@@ -170,6 +175,17 @@ int rf_op_timestep_embed(const void* t, float pre_scale, void* out, int batch, v
   return rf::timestep_embed_launch(static_cast<const bf16*>(t), nullptr, 1, pre_scale,
                                    static_cast<bf16*>(out), batch,
                                    static_cast<cudaStream_t>(stream));
+}
+
+int rf_op_resize_u8(const uint8_t* in_hwc, int H, int W, uint8_t* tmp, uint8_t* out_hwc, int out_h,
+                    int out_w, const int* bounds_x, const int* coef_x, int ksize_x, const int* bounds_y,
+                    const int* coef_y, int ksize_y, void* stream) {
+  if (!in_hwc || !tmp || !out_hwc || !bounds_x || !coef_x || !bounds_y || !coef_y) {
+    rf::set_error("rf_op_resize_u8: null operand");
+    return -1;
+  }
+  return rf::resize_u8_launch(in_hwc, H, W, tmp, out_hwc, out_h, out_w, bounds_x, coef_x, ksize_x,
+                              bounds_y, coef_y, ksize_y, static_cast<cudaStream_t>(stream));
 }
 
 int rf_op_euler_step(void* x, const void* v, const float* sigmas, const int* step, int n,

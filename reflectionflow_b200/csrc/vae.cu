@@ -57,13 +57,15 @@ __global__ void unpack_latents_kernel(const bf16* __restrict__ packed, bf16* __r
 }
 
 // ------------------------------------------------------------------ GroupNorm(32)
-// stats over the interior of a padded NHWC tensor; one (sum, sumsq) pair per 4-channel subgroup
+// stats over the interior of a padded NHWC tensor; one (sum, sumsq) pair per 4-channel subgroup.
+// Deterministic (no atomics): fixed-order reduction inside the block, one partial row per block,
+// partial rows summed in block order by the finalize kernel — a run-to-run difference in the last
+// bit of a mean could flip a bf16 rounding downstream and with it a candidate's score.
+static constexpr int kGnBlocks = 148 * 4;
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const bf16* __restrict__ x, int H, int W, int C, int padded, double* __restrict__ acc) {
-  extern __shared__ float sm[];  // [2][C/4]
+gn_stats_kernel(const bf16* __restrict__ x, int H, int W, int C, int padded, float* __restrict__ part) {
+  __shared__ float sm[256][4];
   const int nsub = C >> 2, oct = C >> 3;
-  for (int i = threadIdx.x; i < 2 * nsub; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const int pix_per_iter = blockDim.x / oct;
   const int my_oct = threadIdx.x % oct, my_p = threadIdx.x / oct;
   const long long npix = static_cast<long long>(H) * W;
@@ -81,24 +83,31 @@ gn_stats_kernel(const bf16* __restrict__ x, int H, int W, int C, int padded, dou
       s1 += c.x + c.y + d.x + d.y;
       q1 += c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
     }
-    atomicAdd(&sm[2 * my_oct], s0);
-    atomicAdd(&sm[nsub + 2 * my_oct], q0);
-    atomicAdd(&sm[2 * my_oct + 1], s1);
-    atomicAdd(&sm[nsub + 2 * my_oct + 1], q1);
   }
+  sm[threadIdx.x][0] = s0; sm[threadIdx.x][1] = q0; sm[threadIdx.x][2] = s1; sm[threadIdx.x][3] = q1;
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * nsub; i += blockDim.x) atomicAdd(&acc[i], static_cast<double>(sm[i]));
+  if (threadIdx.x < nsub) {  // subgroup sg = 2 * octet + half
+    const int o = threadIdx.x >> 1, hf = threadIdx.x & 1;
+    float s = 0.f, q = 0.f;
+    for (int pp = 0; pp < pix_per_iter; ++pp) {
+      s += sm[pp * oct + o][2 * hf];
+      q += sm[pp * oct + o][2 * hf + 1];
+    }
+    part[static_cast<size_t>(blockIdx.x) * 2 * nsub + threadIdx.x] = s;
+    part[static_cast<size_t>(blockIdx.x) * 2 * nsub + nsub + threadIdx.x] = q;
+  }
 }
-__global__ void gn_finalize_kernel(const double* __restrict__ acc, int C, double count,
+__global__ void gn_finalize_kernel(const float* __restrict__ part, int nblocks, int C, double count,
                                    float* __restrict__ mean_rstd) {
   const int g = threadIdx.x;  // 32 groups
   if (g >= 32) return;
   const int nsub = C >> 2, per = nsub / 32;
   double s = 0, q = 0;
-  for (int i = 0; i < per; ++i) {
-    s += acc[g * per + i];
-    q += acc[nsub + g * per + i];
-  }
+  for (int b = 0; b < nblocks; ++b)
+    for (int i = 0; i < per; ++i) {
+      s += static_cast<double>(part[static_cast<size_t>(b) * 2 * nsub + g * per + i]);
+      q += static_cast<double>(part[static_cast<size_t>(b) * 2 * nsub + nsub + g * per + i]);
+    }
   const double n = count * (C / 32);
   const double mean = s / n;
   double var = q / n - mean * mean;
@@ -358,7 +367,7 @@ struct rf_vae {
   bf16* buf[4] = {nullptr, nullptr, nullptr, nullptr};
   long long tag[4] = {-1, -1, -1, -1};  // geometry (H, W, C) whose zero ring is currently valid
   bf16 *tok = nullptr, *tokx = nullptr, *qkv = nullptr, *S = nullptr, *vt = nullptr, *ao = nullptr, *ay = nullptr;
-  double* gn_acc = nullptr;
+  float* gn_acc = nullptr;  // [kGnBlocks][2 * C/4] block partials
   float* gn_mr = nullptr;
 };
 
@@ -439,14 +448,12 @@ int grid_for(long long work, int threads = 256) {
 int group_norm(rf_vae* h, const bf16* x, bf16* out, int H, int W, const Norm& n, int silu,
                int in_padded, int out_padded, cudaStream_t s) {
   const int C = n.c;
-  const int nsub = C / 4;
-  RF_CHECK_CUDA(cudaMemsetAsync(h->gn_acc, 0, sizeof(double) * 2 * nsub, s));
   {
     rf::ProfScope prof("vae_gn_stats", 0, 2.0 * H * W * C, s);
-    rf::gn_stats_kernel<<<148 * 4, 256, 2 * nsub * sizeof(float), s>>>(x, H, W, C, in_padded, h->gn_acc);
+    rf::gn_stats_kernel<<<rf::kGnBlocks, 256, 0, s>>>(x, H, W, C, in_padded, h->gn_acc);
   }
   RF_CHECK_CUDA(cudaGetLastError());
-  rf::gn_finalize_kernel<<<1, 32, 0, s>>>(h->gn_acc, C, static_cast<double>(H) * W, h->gn_mr);
+  rf::gn_finalize_kernel<<<1, 32, 0, s>>>(h->gn_acc, rf::kGnBlocks, C, static_cast<double>(H) * W, h->gn_mr);
   {
     rf::ProfScope prof("vae_gn_apply", 0, 4.0 * H * W * C, s);
     rf::gn_apply_kernel<<<grid_for(static_cast<long long>(H) * W * (C / 8)), 256, 0, s>>>(
@@ -480,7 +487,7 @@ int ensure_workspace(rf_vae* h, int H, int W) {  // H, W: output image size
   RF_TRYV(valloc(h, &p, ntok * 512 * 2)); h->ao = static_cast<bf16*>(p);
   RF_TRYV(valloc(h, &p, ntok * 512 * 2)); h->ay = static_cast<bf16*>(p);
   if (!h->gn_acc) {
-    RF_TRYV(valloc(h, &p, sizeof(double) * 2 * 128)); h->gn_acc = static_cast<double*>(p);
+    RF_TRYV(valloc(h, &p, sizeof(float) * 2 * 128 * rf::kGnBlocks)); h->gn_acc = static_cast<float*>(p);
     RF_TRYV(valloc(h, &p, sizeof(float) * 64)); h->gn_mr = static_cast<float*>(p);
   }
   h->ws_h = H; h->ws_w = W;

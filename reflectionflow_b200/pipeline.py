@@ -51,7 +51,8 @@ class Condition:
     generator (pipeline_tools.py:10), which is not reproducible."""
 
     def __init__(self, condition_type: str = "cot", raw_img=None, condition=None, mask=None,
-                 position_delta=None, latents: Optional[torch.Tensor] = None):
+                 position_delta=None, latents: Optional[torch.Tensor] = None,
+                 eps: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None):
         if condition_type not in condition_dict:
             raise NotImplementedError(f"Condition type {condition_type} not implemented")
         assert mask is None, "Mask not supported yet"
@@ -60,6 +61,7 @@ class Condition:
         self.condition = condition if condition is not None else raw_img
         self.position_delta = position_delta
         self.latents = latents
+        self.eps, self.generator = eps, generator  # posterior noise of the VAE encode (explicit)
 
     @property
     def type_id(self) -> int:
@@ -71,7 +73,7 @@ class Condition:
             side = int(round(tokens.shape[1] ** 0.5))
             ids = pipe._prepare_latent_image_ids(tokens.shape[0], side, side, pipe.device, pipe.dtype)
         else:
-            tokens, ids = pipe.encode_images(self.condition)
+            tokens, ids = pipe.encode_images(self.condition, eps=self.eps, generator=self.generator)
         ids = ids.clone()
         if self.position_delta is not None:
             ids[:, 1] += self.position_delta[0]
@@ -244,11 +246,29 @@ class B200FluxPipeline:
         noise = torch.randn(shape, generator=generator, device=gdev, dtype=dtype).to(device)
         return self._pack_latents(noise, batch_size, num_channels_latents, height, width), ids
 
-    def encode_images(self, images):
-        """train_flux/flux/pipeline_tools.py:7-30 — needs the VAE encoder (next tier)."""
-        raise NotImplementedError(
-            "VAE encode is not native yet (SURVEY.md §8f): construct Condition(latents=...) with the "
-            "packed, shifted and scaled condition latents")
+    def encode_images(self, images, eps: Optional[torch.Tensor] = None,
+                      generator: Optional[torch.Generator] = None):
+        """train_flux/flux/pipeline_tools.py:7-30: preprocess -> vae.encode -> posterior sample ->
+        (z - shift) * scale -> pack, + position ids.  `images`: PIL image(s) or uint8 [B, H, W, 3]
+        (sizes must be multiples of 16).  The posterior noise is `eps` (bf16 [16, H/8, W/8]) or drawn
+        from `generator`; with neither it comes from the global CPU RNG (the reference samples it
+        with no generator at all, App. B.4)."""
+        if self.vae is None:
+            raise NotImplementedError("no VAE attached: construct Condition(latents=...) or build the "
+                                      "pipeline with vae=B200AutoencoderKL(...)")
+        if not torch.is_tensor(images):
+            imgs = images if isinstance(images, (list, tuple)) else [images]
+            images = torch.stack([torch.from_numpy(np.array(im.convert("RGB"))) for im in imgs])
+        if images.dim() == 3:
+            images = images[None]
+        B, H, W, _ = images.shape
+        if H % 16 or W % 16:
+            raise ValueError("condition image sides must be multiples of 16")
+        if eps is None:
+            eps = torch.randn((16, H // 8, W // 8), generator=generator, dtype=self.dtype)
+        tokens = self.vae.encode_packed(images, eps)
+        ids = self._prepare_latent_image_ids(B, H // 16, W // 16, self.device, self.dtype)
+        return tokens, ids
 
     # ------------------------------------------------------------------ the denoise call
     def _denoise(self, latents, prompt_embeds, pooled, text_ids, image_ids, num_inference_steps,
@@ -285,6 +305,8 @@ class B200FluxPipeline:
                 image = self.vae.decode_packed(latents, height, width, "u8").cpu().numpy().astype("float32") / 255.0
             elif output_type == "pt":
                 image = self.vae.decode_packed(latents, height, width, "pt")
+            elif output_type == "u8":  # extension: uint8 [B, H, W, 3] left on the device
+                image = self.vae.decode_packed(latents, height, width, "u8")
             else:
                 raise ValueError(f"output_type {output_type!r} not supported")
         if not return_dict:

@@ -13,7 +13,7 @@ import torch
 
 from . import search as S
 from .dist import DistCtx
-from .reflectionflow import _save_candidate, build_pipeline
+from .reflectionflow import _ensure_pixels, _save_candidate, build_pipeline
 from .utils import TORCH_DTYPE_MAP, get_latent_prep_fn, get_noises, parse_cli_args
 from .verifiers import Candidate
 
@@ -37,14 +37,12 @@ def sample(noises: Dict[int, torch.Tensor], prompts: List[str], search_round: in
             print(f"Generating images for batch with seeds: {seeds_batch}.")
         batched_latents = torch.stack([noise_items[i][1] for i in idxs]).squeeze(dim=1)
         batched_prompts = [prompts[i] for i in idxs]
-        no_vae = getattr(pipe, "vae", None) is None
         res = pipe(prompt=batched_prompts, latents=batched_latents,
                    guidance_scale=pa["guidance_scale"], num_inference_steps=pa["num_inference_steps"],
-                   height=pa["height"], width=pa["width"], output_type="latent" if no_vae else "pil")
+                   height=pa["height"], width=pa["width"], output_type="latent")
         for j, i in enumerate(idxs):
-            lat = res.images[j:j + 1] if no_vae else None
-            img = None if no_vae else res.images[j]
-            c = Candidate(names[i], noise_items[i][0], latents=lat, image=img)
+            c = Candidate(names[i], noise_items[i][0], latents=res.images[j:j + 1])
+            _ensure_pixels(pipe, c, pa["height"], pa["width"])
             _save_candidate(c, names[i])
             local.append((i, c))
     return {"prompt": original_prompt, "search_round": search_round, "num_noises": len(noises),

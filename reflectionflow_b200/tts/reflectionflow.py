@@ -10,10 +10,10 @@ What changes, and why:
   * the boundary is explicit: init noise = the `noises` the caller sampled (the reference samples
     them but never passes them on, App. B.1), condition latents are given tensors (the reference
     samples the VAE posterior, B.4);
-  * images cross rounds as latents in HBM, not PNG files re-opened from disk; PNGs are written only
-    when a VAE is attached.  Until VAE decode/encode are native, the 512x512 condition of a parent
-    is formed in latent space (2x2 average pool of the parent's 128x128 latent grid) — a labelled
-    stand-in for decode -> resize -> encode.
+  * images cross rounds in HBM, not as PNG files re-opened from disk: with a VAE attached the
+    parent -> condition step is decode -> PIL-exact BICUBIC resize -> encode, all on the device
+    (PNGs are still written for downstream tools); without a VAE the 512x512 condition is formed in
+    latent space (area average of the parent's latent grid) — a labelled stand-in.
 Artefact layout and names (midimg/<round>_round@<seed>.png, best_img_meta.jsonl,
 best_img_detailedscore.jsonl, samples_best/, samples_lastround/, samples_path_bestround/) follow the
 reference so downstream tools keep working."""
@@ -54,10 +54,36 @@ def parent_condition_latents(parent_latents: torch.Tensor, height: int, width: i
 
 
 def _save_candidate(cand: Candidate, path: str):
-    if cand.image is not None:
-        cand.image.save(path)
-    else:
+    """PNG when the candidate has pixels (VAE attached), always the packed latent next to it (the
+    next stage reloads candidates from `*.latent.pt`, not by re-encoding PNGs)."""
+    if cand.pil() is not None:
+        cand.pil().save(path)
+    if cand.latents is not None:
         torch.save(cand.latents.cpu(), os.path.splitext(path)[0] + ".latent.pt")
+
+
+def _ensure_pixels(pipe, cand: Candidate, height: int, width: int):
+    if cand.image_u8 is None and getattr(pipe, "vae", None) is not None:
+        cand.image_u8 = pipe.vae.decode_packed(cand.latents.reshape(1, -1, cand.latents.shape[-1]),
+                                               height, width, "u8")[0]
+    return cand.image_u8
+
+
+def parent_condition(pipe, parent: Candidate, height: int, width: int, cond_size: int, seed: int):
+    """tts_reflectionflow.py:273-279: the parent IMAGE, resized to condition_size, becomes the `cot`
+    condition.  With a VAE attached this is the real path, all on the device: decode -> PIL-exact
+    BICUBIC resize -> encode (posterior noise seeded by the candidate's seed).  Without one, a
+    latent-space area average stands in (labelled in the module docstring)."""
+    position_delta = [0, -cond_size // 16]
+    if getattr(pipe, "vae", None) is None:
+        return Condition("cot", latents=parent_condition_latents(parent.latents, height, width, cond_size),
+                         position_delta=position_delta)
+    from ..resize import resize_u8
+    u8 = _ensure_pixels(pipe, parent, height, width)
+    small = resize_u8(u8[None], cond_size, cond_size)
+    eps = torch.randn((16, cond_size // 8, cond_size // 8), generator=torch.Generator().manual_seed(int(seed)),
+                      dtype=torch.bfloat16)
+    return Condition("cot", condition=small, position_delta=position_delta, eps=eps)
 
 
 def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
@@ -146,7 +172,6 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
     else:
         prompts = [original_prompt] * num_samples
     cond_size = pa["condition_size"]
-    position_delta = [0, -cond_size // 16]
 
     # ---- 7. regenerate: my share of the candidates, one full trajectory each
     t0 = time.time()
@@ -156,15 +181,11 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
     for i in ctx.my_candidates(num_samples):
         seed, noise = noise_items[i]
         parent = selected[i]
-        cond_lat = parent_condition_latents(parent.latents, pa["height"], pa["width"], cond_size)
-        cond = Condition("cot", latents=cond_lat, position_delta=position_delta)
+        cond = parent_condition(pipe, parent, pa["height"], pa["width"], cond_size, seed)
         result = generate_fn(pipe, prompt=[prompts[i]], conditions=[cond], height=pa["height"],
                              width=pa["width"], model_config=config.get("model", None),
-                             default_lora=True, latents=noise,
-                             output_type="latent" if getattr(pipe, "vae", None) is None else "pil")
-        lat = result.images if getattr(pipe, "vae", None) is None else None
-        img = None if lat is not None else result.images[0]
-        new_local.append((i, Candidate(full_imgnames[i], seed, latents=lat, image=img)))
+                             default_lora=True, latents=noise, output_type="latent")
+        new_local.append((i, Candidate(full_imgnames[i], seed, latents=result.images)))
     if rank0:
         print(f"Time taken for image generation: {time.time() - t0} seconds")
 
@@ -175,8 +196,8 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
                                  torch.bfloat16)
     new_cands = [Candidate(full_imgnames[i], noise_items[i][0], latents=all_lat[i])
                  for i in range(num_samples)]
-    for i, c in new_local:
-        new_cands[i].image = c.image
+    for i, _c in new_local:  # each rank decodes (VAE attached) and stores its own candidates
+        _ensure_pixels(pipe, new_cands[i], pa["height"], pa["width"])
         _save_candidate(new_cands[i], full_imgnames[i])
     t0 = time.time()
     mine = ctx.my_candidates(num_samples)
@@ -255,10 +276,10 @@ def build_pipeline(config: dict, args, ctx: DistCtx):
         raise RuntimeError("no FLUX.1-dev checkpoint is reachable offline: run with --synthetic, or "
                            "build B200FluxPipeline.from_state_dict(...) yourself and call sample()")
     pipe = B200FluxPipeline.from_synthetic(cfg, seed=0, device=ctx.device,
-                                           lora_rank=32 if lora_path is not None else 0)
+                                           lora_rank=32 if lora_path is not None else 0, with_vae=True)
     pipe.text_encoder_hook = HashTextEncoder(cfg.joint_attention_dim, cfg.pooled_projection_dim)
     if lora_path is not None:
-        pipe.load_lora_weights(synthetic_lora(cfg, seed=1), adapter_name="reflection")
+        pipe.transformer.load_lora(synthetic_lora(cfg, seed=1), mode="merged")
     pipe.set_progress_bar_config(disable=True)
     return pipe
 

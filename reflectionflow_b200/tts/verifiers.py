@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import hashlib
 import math
+import os
 from typing import Any, Dict, List, Optional, Sequence
 
 import torch
@@ -22,9 +23,16 @@ class Candidate:
     final latent (always) and decoded image (when a VAE is attached)."""
 
     def __init__(self, name: str, seed: int, latents: Optional[torch.Tensor] = None, image=None,
-                 stub_score: Optional[float] = None):
+                 stub_score: Optional[float] = None, image_u8: Optional[torch.Tensor] = None):
         self.name, self.seed, self.latents, self.image = name, int(seed), latents, image
         self.stub_score = stub_score
+        self.image_u8 = image_u8  # decoded uint8 [H, W, 3] on the device (when a VAE is attached)
+
+    def pil(self):
+        if self.image is None and self.image_u8 is not None:
+            from PIL import Image
+            self.image = Image.fromarray(self.image_u8.cpu().numpy())
+        return self.image
 
 
 def latent_functional(latents: torch.Tensor) -> float:
@@ -111,7 +119,8 @@ class StubReflector:
     def generate_reflections(self, cands, original_prompt, current_prompts, reflections, evaluations):
         out = []
         for c, ev in zip(cands, evaluations):
-            h = hashlib.sha256((c.name + ev).encode()).hexdigest()[:6]
+            ev_ = ev.replace(c.name, os.path.basename(c.name))  # independent of the output directory
+            h = hashlib.sha256((os.path.basename(c.name) + ev_).encode()).hexdigest()[:6]
             out.append(f"Make the subject match the prompt more closely ({h}).")
         return out
 

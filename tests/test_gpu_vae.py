@@ -85,3 +85,16 @@ def test_postprocess_is_bit_exact_on_given_image():
     t = (x / 2 + 0.5).clamp(0, 1).float()
     got = torch.round(t * 255).to(torch.uint8).permute(0, 2, 3, 1)
     assert torch.equal(want, got)
+
+
+@pytest.mark.parametrize("hw,out", [((1024, 1024), (512, 512)), ((256, 384), (128, 192)), ((100, 60), (37, 45))])
+def test_resize_is_bit_identical_to_pil(hw, out):
+    """device BICUBIC resize == PIL.Image.resize (the parent -> 512x512 condition step)"""
+    import numpy as np
+    from PIL import Image
+    from reflectionflow_b200.resize import resize_u8
+    rng = np.random.default_rng(hw[0] + out[1])
+    img = rng.integers(0, 256, size=(hw[0], hw[1], 3), dtype=np.uint8)
+    want = np.array(Image.fromarray(img).resize((out[1], out[0])))
+    got = resize_u8(torch.from_numpy(img)[None].cuda(), out[0], out[1])[0].cpu().numpy()
+    assert np.array_equal(got, want)
