@@ -195,6 +195,34 @@ int rf_profile_stop(char* json_out, int capacity);
 /* number of kernels this library launched since process start (for bench.py's gpu_launches) */
 int64_t rf_launch_count(void);
 
+/* ---- text encoders (T5 encoder + CLIP text model) --------------------------------------------
+ * Replaces `pipe.text_encoder_2(ids)[0]` and `pipe.text_encoder(ids).pooler_output` inside diffusers
+ * FluxPipeline.encode_prompt, called once per candidate prompt from train_flux/flux/generate.py:148-161
+ * (via pipeline_tools.py:33-52); every reflection candidate carries its own refined prompt
+ * (tts/tts_reflectionflow.py:286-294).  Token ids in (tokenisation stays on the host), embeddings out.
+ * Rounding points follow the transformers "eager" attention path (T5Attention / CLIPAttention). */
+typedef struct rf_text rf_text;
+typedef struct rf_text_config {
+  int t5_layers, t5_d_model, t5_d_ff, t5_heads, t5_vocab; /* T5-v1.1-XXL: 24, 4096, 10240, 64, 32128; d_kv = 64 */
+  float t5_eps;                                           /* 1e-6 */
+  int clip_layers, clip_d_model, clip_heads, clip_vocab, clip_max_pos; /* CLIP-L: 12, 768, 12, 49408, 77 */
+} rf_text_config;
+
+int rf_text_create(const rf_text_config* cfg, rf_text** out);
+void rf_text_destroy(rf_text* h);
+/* key = "t5." + T5EncoderModel state-dict key, or "clip." + CLIPTextModel state-dict key; src = device bf16 */
+int rf_text_load_weight(rf_text* h, const char* key, const void* src, int64_t numel);
+/* number of keys under `prefix` ("t5." / "clip.") not loaded yet (names in rf_last_error) */
+int rf_text_missing_weights(rf_text* h, const char* prefix);
+/* ids: device int32 [batch, seq]; position_bias: device bf16 [heads, seq, seq] (layer-0 relative
+ * attention bias, shared by all layers; bucketed on the host); out: device bf16 [batch, seq, d_model] */
+int rf_t5_encode(rf_text* h, const int* ids, int batch, int seq, const void* position_bias, void* out,
+                 void* stream);
+/* ids: device int32 [batch, seq <= 77]; eos_pos: device int32 [batch] (pooling position, = ids.argmax(-1)
+ * for the stock CLIP-L config); pooled_out bf16 [batch, d_model]; hidden_out (nullable) bf16 [batch, seq, d_model] */
+int rf_clip_encode(rf_text* h, const int* ids, const int* eos_pos, int batch, int seq, void* pooled_out,
+                   void* hidden_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,18 @@ def _declare(lib):
         lib.rf_vae_decode.argtypes = [vp, vp, ci, ci, cf, cf, vp, vp, vp]
         lib.rf_vae_encode.restype = ci
         lib.rf_vae_encode.argtypes = [vp, vp, vp, ci, ci, vp, cf, cf, vp, vp]
+    lib.rf_text_create.restype = ci
+    lib.rf_text_create.argtypes = [vp, POINTER(vp)]
+    lib.rf_text_destroy.restype = None
+    lib.rf_text_destroy.argtypes = [vp]
+    lib.rf_text_load_weight.restype = ci
+    lib.rf_text_load_weight.argtypes = [vp, c_char_p, vp, c_int64]
+    lib.rf_text_missing_weights.restype = ci
+    lib.rf_text_missing_weights.argtypes = [vp, c_char_p]
+    lib.rf_t5_encode.restype = ci
+    lib.rf_t5_encode.argtypes = [vp, vp, ci, ci, vp, vp, vp]
+    lib.rf_clip_encode.restype = ci
+    lib.rf_clip_encode.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp]
     if hasattr(lib, "rf_dit_create"):
         lib.rf_dit_create.restype = ci
         lib.rf_dit_create.argtypes = [vp, POINTER(vp)]
