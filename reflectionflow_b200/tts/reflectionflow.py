@@ -277,7 +277,16 @@ def build_pipeline(config: dict, args, ctx: DistCtx):
                            "build B200FluxPipeline.from_state_dict(...) yourself and call sample()")
     pipe = B200FluxPipeline.from_synthetic(cfg, seed=0, device=ctx.device,
                                            lora_rank=32 if lora_path is not None else 0, with_vae=True)
-    pipe.text_encoder_hook = HashTextEncoder(cfg.joint_attention_dim, cfg.pooled_projection_dim)
+    if getattr(args, "text_encoders", "hash") == "native":
+        # T5-v1.1-XXL + CLIP-L of the real shapes (random init), ids from a byte tokenizer stand-in
+        from ..text import B200TextEncoders
+        from .verifiers import ByteTokenizer
+        enc = B200TextEncoders(device=ctx.device).init_synthetic_weights(seed=2)
+        pipe.text_encoders = enc
+        pipe.text_encoder_hook = enc.as_hook(ByteTokenizer(49408, eos=49407, pad=49407, bos=49406),
+                                             ByteTokenizer(32128, eos=1, pad=0))
+    else:
+        pipe.text_encoder_hook = HashTextEncoder(cfg.joint_attention_dim, cfg.pooled_projection_dim)
     if lora_path is not None:
         pipe.transformer.load_lora(synthetic_lora(cfg, seed=1), mode="merged")
     pipe.set_progress_bar_config(disable=True)

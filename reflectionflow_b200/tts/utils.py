@@ -31,6 +31,8 @@ def parse_cli_args(argv=None):
                         help="seed the global RNG (the reference leaves it unseeded)")
     parser.add_argument("--synthetic", action="store_true",
                         help="random-init weights + hash text embeddings + stub verifier (no network)")
+    parser.add_argument("--text_encoders", choices=("hash", "native"), default="hash",
+                        help="--synthetic only: hash embeddings, or random-init T5-XXL + CLIP-L run on the device")
     parser.add_argument("--layers", type=str, default=None, help="debug: 'double,single' layer counts")
     return parser.parse_args(argv)
 

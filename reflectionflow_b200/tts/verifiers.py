@@ -147,3 +147,20 @@ class HashTextEncoder:
             embs.append(torch.randn(max_sequence_length, self.joint_dim, generator=g2))
             pooled.append(torch.randn(self.pooled_dim, generator=g1))
         return torch.stack(embs).to(torch.bfloat16), torch.stack(pooled).to(torch.bfloat16)
+
+
+class ByteTokenizer:
+    """Offline stand-in for the CLIP BPE / T5 sentencepiece tokenizers (their vocabularies are
+    checkpoint assets): UTF-8 bytes offset into the vocabulary, EOS, padding.  Same call shape as
+    the tokenizer arguments of B200TextEncoders.as_hook: (prompts, max_len) -> LongTensor ids."""
+
+    def __init__(self, vocab: int, eos: int, pad: int, bos: Optional[int] = None):
+        self.vocab, self.eos, self.pad, self.bos = vocab, eos, pad, bos
+
+    def __call__(self, prompts: List[str], max_len: int) -> torch.Tensor:
+        out = torch.full((len(prompts), max_len), self.pad, dtype=torch.long)
+        for i, p in enumerate(prompts):
+            toks = ([self.bos] if self.bos is not None else []) + [3 + b % (self.vocab - 4) for b in p.encode()]
+            toks = toks[: max_len - 1] + [self.eos]
+            out[i, : len(toks)] = torch.tensor(toks)
+        return out
