@@ -25,6 +25,7 @@ static constexpr int kTile = 128;
 static constexpr int kHalfBytes = kTile * 128;   // one [128 x 64] bf16 box = 16 KB
 static constexpr int kTileBytes = 2 * kHalfBytes;  // [128 x 128] bf16 = 32 KB
 static constexpr int kKVStages = 2;
+static constexpr int kPolyEvery = 2;  // every n-th exp2 pair on the FMA pipe (0 = all on MUFU)
 static constexpr int kAttnSmem = (2 + 2 * kKVStages) * kTileBytes + 1024 + 256;
 
 struct alignas(64) AttnParamsDev {
@@ -75,6 +76,7 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
   uint64_t* p_hi = bars + 13;     // [2] per query tile: P of kv rows 64..127 written
   uint64_t* o_full = bars + 15;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* s_scale = reinterpret_cast<float*>(bars + 17);  // scale_log2, re-read after the p_lo arrive (see softmax)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,6 +109,7 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
       mbar_init(&p_hi[i], 4);
     }
     mbar_init(o_full, 1);
+    *s_scale = p.scale_log2;
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -270,13 +273,9 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
         for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, s[c]);
         tmem_ld_wait();
         if ((warp & 3) == 0 && lane == 0) RF_TR(5 + 4 * t, j);
-        if (kv_valid < kTile) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= kv_valid) s[c][i] = 0xff800000u;  // -inf
-        }
+        // Keys past n_tok (last, partial tile): TMA zero-fills those K and V rows, so their scores
+        // are exactly 0 and their P V contribution vanishes; only the row sum needs a correction
+        // (below).  No per-element masking: that cost 254 ISETP/SEL per tile on every tile.
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -307,34 +306,72 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
           }
         }
         have = true;
-        // P = exp2(s * scale + bias - m_used), two elements per instruction (FFMA2 / FADD2)
+        // P = exp2(s * scale + bias - m_used), two elements per instruction (FFMA2 / FADD2).
+        // One warp can issue a MUFU.EX2 every 8 cycles at best (tools/mufu_rate.cu), 1024 cycles for
+        // the 128 values of a row, and this phase is on the critical path of the tile
+        // (QK^T -> softmax -> PV -> next QK^T).  Every kPolyEvery-th pair is therefore evaluated on
+        // the FMA pipe instead: round-to-nearest split x = n + f (magic-number add), 2^f by a cubic
+        // (rel. error 7.7e-5, 50x below the bf16 rounding of P), 2^n by an integer add into the
+        // exponent field.
         const float neg_m = bias - m_used;
-        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
         const float2 nm2 = make_float2(neg_m, neg_m);
         float2 l2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        auto exp_chunk = [&](int c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float2 x = __ffma2_rn(
+            float2 x = __ffma2_rn(
                 make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
             float2 e;
-            e.x = ex2_approx(x.x);
-            e.y = ex2_approx(x.y);
+            if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1)) {
+              x.x = fmaxf(x.x, -125.0f);
+              x.y = fmaxf(x.y, -125.0f);
+              const float2 magic = make_float2(12582912.0f, 12582912.0f);
+              const float2 t2 = __fadd2_rn(x, magic);                       // low mantissa bits = round(x)
+              const float2 n2 = __fadd2_rn(t2, make_float2(-12582912.0f, -12582912.0f));
+              const float2 f2 = __ffma2_rn(n2, make_float2(-1.0f, -1.0f), x);  // [-0.5, 0.5]
+              float2 q = __ffma2_rn(make_float2(0.05508868396282196f, 0.05508868396282196f), f2,
+                                    make_float2(0.24260404706001282f, 0.24260404706001282f));
+              q = __ffma2_rn(q, f2, make_float2(0.6932762265205383f, 0.6932762265205383f));
+              q = __ffma2_rn(q, f2, make_float2(0.9999289512634277f, 0.9999289512634277f));
+              e.x = __uint_as_float(__float_as_uint(q.x) + (__float_as_uint(t2.x) << 23));
+              e.y = __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(t2.y) << 23));
+            } else {
+              e.x = ex2_approx(x.x);
+              e.y = ex2_approx(x.y);
+            }
             l2 = __fadd2_rn(l2, e);
             pk[i] = pack_bf16x2(e.x, e.y);
           }
           tmem_st_32x16(tS + c * 16, pk);
-          if (c == 1) {  // P of kv rows 0..63 complete: PV can start on it while the rest is computed
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_lo[t]);
-          }
+        };
+        if (warp == 0 && lane == 0) RF_TR(12, j);
+        exp_chunk(0);
+        exp_chunk(1);
+        if (warp == 0 && lane == 0) RF_TR(13, j);
+        exp_chunk(2);
+        // P of kv rows 0..63 was stored two chunks ago: the wait below no longer stalls the MUFU
+        // stream, and PV can start on the first half while the last chunk is computed
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_lo[t]);
+        {
+          // keep the last chunk's exponentials BEHIND the arrive: ptxas otherwise hoists every
+          // MUFU.EX2 above the first STTM and the early signal is lost.  A shared-memory load
+          // cannot move above the arrive, and the last chunk's FFMA2 depend on its value.
+          float sc_b;
+          asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(sc_b) : "r"(smem_u32(s_scale)) : "memory");
+          sc2 = make_float2(sc_b, sc_b);
         }
-        const float l0 = l2.x, l1 = l2.y;
-        l_sum += l0 + l1;
+        if (warp == 0 && lane == 0) RF_TR(14, j);
+        exp_chunk(3);
+        if (warp == 0 && lane == 0) RF_TR(15, j);
+        float l_tile = l2.x + l2.y;
+        if (kv_valid < kTile)  // zero-score padding keys: each added exp2(0 * scale + neg_m) to the sum
+          l_tile -= static_cast<float>(kTile - kv_valid) * ex2_approx(neg_m);
+        l_sum += l_tile;
       }
       if ((warp & 3) == 0 && lane == 0) RF_TR(6 + 4 * t, j);
       tmem_st_wait();

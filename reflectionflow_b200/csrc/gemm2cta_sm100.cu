@@ -16,6 +16,7 @@
 // [128 rows x 64 cols] -> TMA store (coalesced, asynchronous, clips ragged M); the residual of the
 // gate+residual epilogue is prefetched by TMA one chunk ahead into smem.  Tiles are rastered in
 // 12-tile-wide column bands so a wave's W slice (19 MB at K=3072) stays L2-resident.
+#include <cstdlib>
 #include <cuda.h>
 
 #include "rf_internal.h"
@@ -62,6 +63,8 @@ __device__ __forceinline__ PixTile pix_tile(const Gemm2Group& G, int m) {
 struct alignas(64) Gemm2Params {
   Gemm2Group g[kMaxGroups2];
   int ngroups, N, K, n_tiles, total_tiles, num_kb, band, bn;
+  long long* trace;  // dev-only per-tile timeline of pair 0 (rf_dbg_set_gemm_trace)
+  int dbg_skip;      // dev-only: 1 = skip the W loads, 2 = skip the A loads (timing experiments; results are garbage)
 };
 struct Tile2 {
   int g, m0, n0;  // m0: first row of the 256-row pair tile, n0: first column
@@ -211,8 +214,9 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * kStage;
-        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStage);
-        if (G.conv_w != 0) {
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], p.dbg_skip == 1 ? 2 * kStageA : p.dbg_skip == 2 ? 2 * Cfg2<kBN>::kStageB : 2 * kStage);
+        if (p.dbg_skip == 2) {
+        } else if (G.conv_w != 0) {
           const int tap = kb / G.conv_cin_blocks;
           const int c0 = (kb - tap * G.conv_cin_blocks) * kBK;
           const int ky = G.conv_taps == 9 ? tap / 3 : 1, kx = G.conv_taps == 9 ? tap % 3 : 1;
@@ -222,7 +226,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         } else {
           tma_load_2d_2cta(sa, &G.tmA, &full_bar[stage], kb * kBK, my_m);
         }
-        tma_load_2d_2cta(sa + kStageA, &G.tmB, &full_bar[stage], kb * kBK, my_n);
+        if (p.dbg_skip != 1) tma_load_2d_2cta(sa + kStageA, &G.tmB, &full_bar[stage], kb * kBK, my_n);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -233,12 +237,23 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = pair; t < p.total_tiles; t += npairs) {
+    const bool tr = p.trace != nullptr && pair == 0;
+    int ti = 0;
+    for (int t = pair; t < p.total_tiles; t += npairs, ++ti) {
+      if (tr && ti < 16) p.trace[ti * 8 + 0] = clock64();
       mbar_wait(&tempty_bar[as], aphase ^ 1);
+      if (tr && ti < 16) p.trace[ti * 8 + 1] = clock64();
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kBN;
+      long long stall = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        if (tr) {
+          const long long c0 = clock64();
+          mbar_wait(&full_bar[stage], phase);
+          stall += clock64() - c0;
+        } else {
+          mbar_wait(&full_bar[stage], phase);
+        }
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * kStage);
         const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
@@ -250,6 +265,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       tc_commit_2cta(&tfull_bar[as], 3);  // accumulator complete in both CTAs
+      if (tr && ti < 16) { p.trace[ti * 8 + 2] = stall; p.trace[ti * 8 + 3] = clock64(); }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -274,13 +290,17 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         }
       }
     }
-    for (int t = pair; t < p.total_tiles; t += npairs) {
+    const bool etr = p.trace != nullptr && pair == 0 && leader && issuer;
+    int eti = 0;
+    for (int t = pair; t < p.total_tiles; t += npairs, ++eti) {
       const Tile2 tc = decode2(p, t);
       const Gemm2Group& G = p.g[tc.g];
       const int my_m = tc.m0 + rank * kRows;
       const int row = my_m + r_in;
       const int row_c = row < G.M ? row : G.M - 1;  // clamped row for direct global reads
+      if (etr && eti < 16) p.trace[eti * 8 + 7] = clock64();
       mbar_wait(&tfull_bar[as], aphase);
+      if (etr && eti < 16) p.trace[eti * 8 + 4] = clock64();
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_off + as * kBN;
 
@@ -425,6 +445,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+      if (etr && eti < 16) p.trace[eti * 8 + 5] = clock64();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (issuer) tma_store_wait_all<0>();  // all boxes written to global before the kernel ends
@@ -456,8 +477,15 @@ int gemm2_init() {
              : 0;
 }
 
+long long* dbg_get_gemm_trace();
 template <int EPI, int BN>
-static int launch2(const Gemm2Params& p, int pairs, double rows, cudaStream_t stream) {
+static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t stream) {
+  Gemm2Params p = p_in;
+  p.trace = dbg_get_gemm_trace();
+  {
+    static const int skip = getenv("RF_DBG_GEMM_SKIP") ? atoi(getenv("RF_DBG_GEMM_SKIP")) : 0;
+    p.dbg_skip = skip;
+  }
   if (int rc = set_attr2<EPI, BN>()) return rc;
   static const char* kNames[4] = {"gemm_bias", "gemm_gelu", "gemm_gate_res", "gemm_qkv_rms_rope"};
   const char* name = p.g[0].conv_w ? (EPI == EPI_GATE_RES ? "conv_res" : "conv_bias") : kNames[EPI];

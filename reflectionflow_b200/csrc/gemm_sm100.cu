@@ -407,6 +407,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 
 static long long* g_gemm_trace = nullptr;
 void dbg_set_gemm_trace(long long* p) { g_gemm_trace = p; }
+long long* dbg_get_gemm_trace() { return g_gemm_trace; }
 int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp,
                  uint32_t box_x, uint32_t box_y, uint32_t stride) {
   PFN_encodeTiled fn = get_encode_fn();

@@ -22,7 +22,7 @@ t = tr.cpu().view(24, 16)
 t0 = int(t[0][t[0] > 0].min())
 names = ["mma:pA", "mma:issuedA", "mma:pB", "mma:issuedB", "A:s_full", "A:ld", "A:exp", "A:arrive",
          "B:s_full", "B:ld", "B:exp", "B:arrive", "A:max", "A:c1st", "A:plo", "A:c3st"]
-print("j  " + " ".join(f"{n:>11s}" for n in names))
+print("j  " + " ".join(f"{n:>8s}" for n in names))
 for j in range(4, 14):
-    print(f"{j:2d} " + " ".join(f"{int(t[j][i]) - t0:11d}" for i in range(16)))
+    print(f"{j:2d} " + " ".join(f"{int(t[j][i]) - t0:8d}" for i in range(16)))
 print("per-iteration period (mma:pA):", [int(t[j + 1][0] - t[j][0]) for j in range(4, 14)])

@@ -28,9 +28,9 @@ def run_case(M, N, K, epi):
     t0 = int(t[0][0])
     ntile = int((t[:, 3] > 0).sum())
     print(f"== M={M} N={N} K={K} epi={epi}: tiles on CTA0 = {ntile}; ideal mainloop/tile = {K//64*512} cycles")
-    print("tile  mma_start  tempty_wait  fullbar_stall  mma_issue_end  epi_start  epi_end  epi_len  prod_stall")
+    print("tile  mma_start  tempty_wait  fullbar_stall  mma_issue_end  epi_start  epi_end  epi_len  epi_wait_from")
     for i in range(ntile):
         r = [int(v) for v in t[i]]
-        print(f"{i:3d} {r[0]-t0:10d} {r[1]-r[0]:11d} {r[2]:13d} {r[3]-t0:13d} {r[4]-t0:10d} {r[5]-t0:8d} {r[5]-r[4]:7d} {r[6]:10d}")
+        print(f"{i:3d} {r[0]-t0:10d} {r[1]-r[0]:11d} {r[2]:13d} {r[3]-t0:13d} {r[4]-t0:10d} {r[5]-t0:8d} {r[5]-r[4]:7d} {r[7]-t0:10d}")
 for c in [(4608, 3072, 3072, 0), (4608, 3072, 3072, 2), (4608, 12288, 3072, 1), (4608, 9216, 3072, 3), (4608, 3072, 15360, 2)]:
     run_case(*c)
