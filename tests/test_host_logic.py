@@ -148,3 +148,29 @@ def test_config_schema_and_cli():
     assert U.TORCH_DTYPE_MAP["bf16"] is torch.bfloat16
     with pytest.raises(KeyError):
         U.get_latent_prep_fn("stabilityai/stable-diffusion-xl-base-1.0")
+
+
+def test_t5_bucket_table_matches_transformers():
+    """host-side relative-position buckets of the native T5 encoder (text.py) vs transformers'"""
+    import torch
+    from transformers.models.t5.modeling_t5 import T5Attention
+    from reflectionflow_b200.text import t5_bucket_table
+    for seq in (1, 7, 77, 128, 512):
+        pos = torch.arange(seq)
+        rel = pos[None, :] - pos[:, None]
+        ref = T5Attention._relative_position_bucket(rel, bidirectional=True, num_buckets=32, max_distance=128)
+        assert torch.equal(t5_bucket_table(seq), ref), seq
+
+
+def test_byte_tokenizer_shapes_and_eos():
+    import torch
+    from reflectionflow_b200.tts.verifiers import ByteTokenizer
+    clip = ByteTokenizer(49408, eos=49407, pad=49407, bos=49406)
+    ids = clip(["a cat", "x" * 200], 77)
+    assert ids.shape == (2, 77) and ids.dtype == torch.long
+    assert ids[0, 0] == 49406 and ids[0, 6] == 49407 and (ids[0, 6:] == 49407).all()
+    assert ids[1, -1] == 49407 and ids.max() < 49408 and ids.min() >= 0
+    assert int(ids[0].argmax()) == 6           # CLIP pools at the first EOS (largest id)
+    t5 = ByteTokenizer(32128, eos=1, pad=0)
+    ids = t5(["hello"], 512)
+    assert ids.shape == (1, 512) and ids[0, 5] == 1 and (ids[0, 6:] == 0).all()
