@@ -106,8 +106,11 @@ __device__ __forceinline__ void linear_round64(const uint32_t (&acc)[64], const 
     float b[8];
     if (bias != nullptr) ld8(bias + q * 8, b);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      v[q * 8 + i] = bf16_round(__uint_as_float(acc[q * 8 + i]) + (bias != nullptr ? b[i] : 0.f));
+    for (int i = 0; i < 8; i += 2) {
+      v[q * 8 + i] = __uint_as_float(acc[q * 8 + i]) + (bias != nullptr ? b[i] : 0.f);
+      v[q * 8 + i + 1] = __uint_as_float(acc[q * 8 + i + 1]) + (bias != nullptr ? b[i + 1] : 0.f);
+      bf16_round2(v[q * 8 + i], v[q * 8 + i + 1]);
+    }
   }
   if (addend != nullptr) {
 #pragma unroll
@@ -115,7 +118,11 @@ __device__ __forceinline__ void linear_round64(const uint32_t (&acc)[64], const 
       float a[8];
       ld8(addend + q * 8, a);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[q * 8 + i] = bf16_round(v[q * 8 + i] + a[i]);
+      for (int i = 0; i < 8; i += 2) {
+        v[q * 8 + i] += a[i];
+        v[q * 8 + i + 1] += a[i + 1];
+        bf16_round2(v[q * 8 + i], v[q * 8 + i + 1]);
+      }
     }
   }
 }
@@ -372,9 +379,14 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
                 float w[8];
                 ld8(nw + c * 64 + q * 8, w);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float y = bf16_round(__fmul_rn(v[q * 8 + i], rinv));  // RMSNorm -> bf16
-                  v[q * 8 + i] = bf16_round(__fmul_rn(y, w[i]));              // * weight -> bf16
+                for (int i = 0; i < 8; i += 2) {
+                  float y0 = __fmul_rn(v[q * 8 + i], rinv), y1 = __fmul_rn(v[q * 8 + i + 1], rinv);
+                  bf16_round2(y0, y1);  // RMSNorm -> bf16
+                  y0 = __fmul_rn(y0, w[i]);
+                  y1 = __fmul_rn(y1, w[i + 1]);
+                  bf16_round2(y0, y1);  // * weight -> bf16
+                  v[q * 8 + i] = y0;
+                  v[q * 8 + i + 1] = y1;
                 }
               }
 #pragma unroll
@@ -423,7 +435,11 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
                          add_r ? add_r + c * 64 : nullptr, v);
           if constexpr (EPI == EPI_GELU) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = gelu_tanh(v[i]);
+            for (int i = 0; i < 64; i += 2) {
+              const float2 g2 = gelu_tanh2(make_float2(v[i], v[i + 1]));
+              v[i] = g2.x;
+              v[i + 1] = g2.y;
+            }
           }
           if constexpr (EPI == EPI_GATE_RES) {
 #pragma unroll
@@ -431,9 +447,11 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
               float gt[8];
               ld8(G.gate + tc.n0 + c * 64 + q * 8, gt);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float gy = bf16_round(__fmul_rn(gt[i], v[q * 8 + i]));
-                v[q * 8 + i] = __fadd_rn(r[q * 8 + i], gy);
+              for (int i = 0; i < 8; i += 2) {
+                float g0 = __fmul_rn(gt[i], v[q * 8 + i]), g1 = __fmul_rn(gt[i + 1], v[q * 8 + i + 1]);
+                bf16_round2(g0, g1);
+                v[q * 8 + i] = __fadd_rn(r[q * 8 + i], g0);
+                v[q * 8 + i + 1] = __fadd_rn(r[q * 8 + i + 1], g1);
               }
             }
           }

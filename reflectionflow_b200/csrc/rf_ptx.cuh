@@ -262,6 +262,14 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// Round two fp32 values to bf16 and back with ONE F2FP.BF16.F32.PACK_AB (FMA-side pipe) + two
+// logic ops.  The scalar form compiles to F2F.BF16.F32, a quarter-rate XU-pipe conversion that the
+// GEMM epilogues would otherwise execute 1-4 times per output element.
+__device__ __forceinline__ void bf16_round2(float& a, float& b) {
+  const uint32_t u = pack_bf16x2(a, b);
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xffff0000u);
+}
 // GELU(tanh) evaluated in fp32 exactly as torch's CPU/CUDA "tanh" approximation does.
 // 0.5 x (1 + tanh(u)) == x * sigmoid(2u) exactly; the sigmoid form needs one ex2 and one rcp (both
 // MUFU, ~1e-7 relative) and has no cancellation for very negative u, where tanhf's 1 + tanh does.
@@ -273,6 +281,21 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * -2.885390081777927f));  // exp(-2u)
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
+}
+// two elements per instruction (FMUL2 / FFMA2 / FADD2); the constants of u and of the exp argument
+// are folded: x * sigmoid(2u), 2u * log2(e) = x * (B + A x^2)
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {
+  const float kB = -2.885390081777927f * 0.7978845608028654f;
+  const float kA = kB * 0.044715f;
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 w = __fmul2_rn(x, __ffma2_rn(make_float2(kA, kA), x2, make_float2(kB, kB)));
+  float2 e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(w.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(w.y));
+  const float2 d = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return __fmul2_rn(x, r);
 }
 
 }  // namespace rf
