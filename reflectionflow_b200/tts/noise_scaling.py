@@ -13,7 +13,7 @@ import torch
 
 from . import search as S
 from .dist import DistCtx
-from .reflectionflow import _ensure_pixels, _save_candidate, build_pipeline
+from .reflectionflow import _ensure_pixels, _save_candidate, build_pipeline, flush_saves
 from .utils import TORCH_DTYPE_MAP, get_latent_prep_fn, get_noises, parse_cli_args
 from .verifiers import Candidate
 
@@ -93,6 +93,8 @@ def main(argv=None, ctx: Optional[DistCtx] = None):
                                 fn=get_latent_prep_fn(pipeline_name))
             sample(noises=noises, prompts=current_prompts, search_round=rnd, pipe=pipe, config=config,
                    original_prompt=original_prompt, midimg_path=midimg_path, ctx=ctx)
+    ctx.barrier()
+    flush_saves()
     ctx.barrier()
     return 0
 

@@ -53,13 +53,47 @@ def parent_condition_latents(parent_latents: torch.Tensor, height: int, width: i
     return x.reshape(b, (ch // 2) * (cw // 2), c).to(parent_latents.dtype)
 
 
+_SAVER = None
+_PENDING: Dict[str, "object"] = {}
+
+
+def _submit_save(path: str, job: Callable[[], None]):
+    """Artefact writes run on a small thread pool (PNG deflate releases the GIL) so that they overlap
+    the next candidate's denoise instead of sitting on the critical path; writes to the same path keep
+    their order.  `flush_saves()` joins them."""
+    global _SAVER
+    if _SAVER is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _SAVER = ThreadPoolExecutor(max_workers=int(os.environ.get("RF_SAVE_THREADS", "8")))
+    prev = _PENDING.get(path)
+
+    def run():
+        if prev is not None:
+            prev.result()  # submitted earlier, hence already running or done: cannot deadlock
+        job()
+    _PENDING[path] = _SAVER.submit(run)
+
+
+def flush_saves():
+    """Block until every artefact submitted so far is on disk (re-raises a failed write)."""
+    pending = list(_PENDING.items())
+    _PENDING.clear()
+    for _path, fut in pending:
+        fut.result()
+
+
 def _save_candidate(cand: Candidate, path: str):
     """PNG when the candidate has pixels (VAE attached), always the packed latent next to it (the
-    next stage reloads candidates from `*.latent.pt`, not by re-encoding PNGs)."""
+    next stage reloads candidates from `*.latent.pt`, not by re-encoding PNGs).  Device->host copies
+    happen here, on the calling thread; encoding and file IO on the save workers."""
     if cand.pil() is not None:
-        cand.pil().save(path)
+        def write_png(c=cand, p=path):
+            with open(p, "wb") as f:
+                f.write(c.png_bytes())
+        _submit_save(path, write_png)
     if cand.latents is not None:
-        torch.save(cand.latents.cpu(), os.path.splitext(path)[0] + ".latent.pt")
+        lat, lp = cand.latents.cpu(), os.path.splitext(path)[0] + ".latent.pt"
+        _submit_save(lp, lambda: torch.save(lat, lp))
 
 
 def _ensure_pixels(pipe, cand: Candidate, height: int, width: int):
@@ -92,7 +126,9 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
            sample_path_lastround: str, sample_path_best: str, sample_path_bestround: str,
            imagetoupdate: List[Candidate], midimg_path: str, total_rounds: int, chains: dict,
            tag: Optional[str] = None, *, verifier=None, reflector=None, ctx: Optional[DistCtx] = None,
-           generate_fn: Callable = _generate) -> dict:
+           generate_fn: Callable = _generate, defer_saves: bool = False) -> dict:
+    """`defer_saves=True` leaves artefact writes in flight when the round returns (they overlap the
+    next round; the caller ends with `flush_saves()`); by default the round's files are on disk."""
     ctx = ctx or DistCtx()
     verifier = verifier or StubVerifier(config["verifier_args"].get("name", "openai"))
     reflector = reflector or StubReflector()
@@ -236,6 +272,8 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
         datapoint["refined_prompt"] = refined_prompt
     if reflection_performed:
         datapoint["reflections"] = update_reflections
+    if not defer_saves:
+        flush_saves()
     return datapoint
 
 
@@ -393,7 +431,7 @@ def main(argv=None, ctx: Optional[DistCtx] = None):
                         sample_path_bestround=dirs["samples_path_bestround"],
                         imagetoupdate=imagetoupdate, midimg_path=dirs["midimg"],
                         tag=meta0.get("tag"), total_rounds=search_rounds, chains=chains,
-                        verifier=verifier, reflector=reflector, ctx=ctx)
+                        verifier=verifier, reflector=reflector, ctx=ctx, defer_saves=True)
             if use_reflection:
                 reflections = dp["reflections"]
             if use_refine:
@@ -402,6 +440,8 @@ def main(argv=None, ctx: Optional[DistCtx] = None):
             chains = dp["chains"]
             if dp["flag_terminated"]:
                 break
+    flush_saves()
+    ctx.barrier()
     return 0
 
 

@@ -13,6 +13,7 @@ from __future__ import annotations
 import hashlib
 import math
 import os
+import threading
 from typing import Any, Dict, List, Optional, Sequence
 
 import torch
@@ -33,6 +34,21 @@ class Candidate:
             from PIL import Image
             self.image = Image.fromarray(self.image_u8.cpu().numpy())
         return self.image
+
+    def png_bytes(self) -> Optional[bytes]:
+        """PNG encoding of the image, computed once per candidate (the round's artefact layout stores
+        the same image under up to four names); thread-safe, callable from the save workers once
+        `pil()` has been materialised on the calling thread."""
+        if self.image is None:
+            return None
+        lock = self.__dict__.setdefault("_png_lock", threading.Lock())
+        with lock:
+            if self.__dict__.get("_png") is None:
+                import io
+                buf = io.BytesIO()
+                self.image.save(buf, format="PNG")
+                self._png = buf.getvalue()
+        return self._png
 
 
 def latent_functional(latents: torch.Tensor) -> float:

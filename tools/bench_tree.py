@@ -48,9 +48,11 @@ def run(n_rounds, parents):
         noises = get_noises(S.MAX_SEED, branch, 1024, 1024)
         dp = RF.sample(noises, "a photo of a cat", upd, refl, rnd, pipe, branch, out, cfg, dirs["last"],
                        dirs["best"], dirs["bestround"], parents, dirs["mid"], n_rounds, chains,
-                       verifier=StubVerifier("nvila"), reflector=StubReflector(), ctx=ctx, generate_fn=gen)
+                       verifier=StubVerifier("nvila"), reflector=StubReflector(), ctx=ctx, generate_fn=gen,
+                       defer_saves=True)
         parents, chains = dp["generated"], dp["chains"]
         upd, refl = dp["refined_prompt"], dp["reflections"]
+    RF.flush_saves()  # every artefact on disk before the clock stops
     return parents
 
 
