@@ -564,7 +564,16 @@ int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups
   p.bn = 256;
   p.n_tiles = N / p.bn;
   p.num_kb = K / kBK;
-  p.band = p.n_tiles < 12 ? p.n_tiles : 12;
+  // raster: tiles run m-major inside bands of `band` n-tiles.  Up to 12 n-tiles (N <= 3072) one band
+  // covers N, so every A row block is read once.  Wider outputs (QKV 36, MLP-in 48 n-tiles) use
+  // narrow bands: the W slice of a band (4 x 256 x K) then stays in L2 for all 18 m-tiles and A
+  // (28 MB) survives between bands; measured DRAM reads per launch, band 12 -> 4 (ncu, B200):
+  // MLP-in 176 -> 112 MB (operands: 104 MB), N = 9216 133 -> 88 MB (85 MB).  Same run time.
+  p.band = p.n_tiles <= 12 ? p.n_tiles : 4;
+  {
+    static const int band_env = getenv("RF_GEMM_BAND") ? atoi(getenv("RF_GEMM_BAND")) : 0;  // dev-only raster experiments
+    if (band_env > 0 && band_env < p.n_tiles) p.band = band_env;
+  }
   int tiles = 0;
   double rows = 0;
   for (int g = 0; g < ngroups; ++g) {
