@@ -364,9 +364,11 @@ def main():
     roofline = {"kernel": dom_name, "bound": "tensor", "achieved": ach,
                 "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
                 "peak_source": pk["source"] + " (sustained cuBLAS bf16)", "traffic": traffic,
-                "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture "
-                                "(profiles/ncu_traffic.json); algorithmic bytes per launch = "
-                                + str(round(dom["bytes"] / dom["launches"])),
+                "traffic_note": "DRAM bytes per launch (launch-weighted over the kernel's shapes) from the "
+                                "committed ncu --set full capture (profiles/ncu_traffic.json, "
+                                "profiles/r01_ncu_v5_summary.md); algorithmic bytes per launch = "
+                                + str(round(dom["bytes"] / dom["launches"]))
+                                + "; the K=12288/15360 launches re-read W once per wave (operands exceed L2)",
                 "launches_per_step": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
                 "share_of_step": dom["ms"] / tot_ms,
                 "how": "CUDA events around every launch of one eager forward inside this run"}
