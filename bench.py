@@ -395,7 +395,7 @@ def main():
                     "note": "same work as `value` plus the copies; the copies are < 1 MB per K-step call, so "
                             "e2e ~= value within run-to-run clock noise (the GPU is power-capped)"},
             "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "clocks": clocks}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and args.gpus == 1:  # the CPU baseline is timed at N=1 only
         leg = cpu_reference_leg(1, 1)
         line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
     _emit(line)

@@ -53,3 +53,20 @@ def test_no_gpu_fails_loudly():
     h = ctypes.c_void_p()
     rc = lib.rf_dit_create(ctypes.byref(cfg), ctypes.byref(h))
     assert rc != 0 and b"no CUDA device" in lib.rf_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly_vae_and_text():
+    from reflectionflow_b200 import _lib
+    from reflectionflow_b200.text import B200TextEncoders
+    from reflectionflow_b200.vae import B200AutoencoderKL
+    with pytest.raises(_lib.RFError):
+        B200TextEncoders()
+    with pytest.raises(_lib.RFError):
+        B200AutoencoderKL()
+    lib = _lib.load()
+    from reflectionflow_b200.text import _TextCfg, T5_XXL, CLIP_L
+    cfg = _TextCfg(**dict(T5_XXL, **CLIP_L))
+    h = ctypes.c_void_p()
+    assert lib.rf_text_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
+    assert b"no CUDA device" in lib.rf_last_error()
