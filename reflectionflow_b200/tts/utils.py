@@ -21,7 +21,7 @@ MODEL_NAME_MAP = {"black-forest-labs/FLUX.1-dev": "flux.1-dev"}
 def parse_cli_args(argv=None):
     """Same flags as tts/utils.py:24-67, plus --seed / --synthetic for offline runs."""
     parser = argparse.ArgumentParser()
-    parser.add_argument("--pipeline_config_path", type=str, default="configs/flux.1_dev_nvilascore.json")
+    parser.add_argument("--pipeline_config_path", type=str, default="configs/headline_tree_flux_dev.json")
     parser.add_argument("--start_index", type=int, default=0)
     parser.add_argument("--end_index", type=int, default=-1)
     parser.add_argument("--imgpath", type=str, default="")

@@ -130,7 +130,7 @@ def test_prepare_latents_cpu_generator_protocol():
 def test_config_schema_and_cli():
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cfg = json.load(open(os.path.join(here, "reflectionflow_b200", "tts", "configs",
-                                      "flux.1_dev_nvilascore.json")))
+                                      "headline_tree_flux_dev.json")))
     for sec in ("pipeline_args", "verifier_args", "refine_args", "search_args", "model",
                 "reflection_args", "prompt_refiner_args", "use_low_gpu_vram", "batch_size_for_img_gen"):
         assert sec in cfg

@@ -16,7 +16,7 @@ ctx = DistCtx.from_env()
 layers = os.environ.get("LAYERS", "19,38")
 steps = int(os.environ.get("STEPS", "28"))
 branch, rounds = int(os.environ.get("BRANCH", "8")), int(os.environ.get("ROUNDS", "4"))
-cfg = json.load(open(os.path.join(os.path.dirname(RF.__file__), "configs", "flux.1_dev_nvilascore.json")))
+cfg = json.load(open(os.path.join(os.path.dirname(RF.__file__), "configs", "headline_tree_flux_dev.json")))
 cfg["search_args"].update(search_branch=branch, search_rounds=rounds)
 cfg["pipeline_args"]["num_inference_steps"] = steps
 
