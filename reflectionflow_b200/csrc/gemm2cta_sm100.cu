@@ -221,9 +221,14 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * kStage;
+#ifdef RF_DEV_HOOKS  // timing experiments of DESIGN.md §9 (make DEV=1): drop one operand stream
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], p.dbg_skip == 1 ? 2 * kStageA : p.dbg_skip == 2 ? 2 * Cfg2<kBN>::kStageB : 2 * kStage);
         if (p.dbg_skip == 2) {
-        } else if (G.conv_w != 0) {
+        } else
+#else
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStage);
+#endif
+        if (G.conv_w != 0) {
           const int tap = kb / G.conv_cin_blocks;
           const int c0 = (kb - tap * G.conv_cin_blocks) * kBK;
           const int ky = G.conv_taps == 9 ? tap / 3 : 1, kx = G.conv_taps == 9 ? tap % 3 : 1;
@@ -233,7 +238,10 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         } else {
           tma_load_2d_2cta(sa, &G.tmA, &full_bar[stage], kb * kBK, my_m);
         }
-        if (p.dbg_skip != 1) tma_load_2d_2cta(sa + kStageA, &G.tmB, &full_bar[stage], kb * kBK, my_n);
+#ifdef RF_DEV_HOOKS
+        if (p.dbg_skip != 1)
+#endif
+        tma_load_2d_2cta(sa + kStageA, &G.tmB, &full_bar[stage], kb * kBK, my_n);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -500,10 +508,12 @@ template <int EPI, int BN>
 static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t stream) {
   Gemm2Params p = p_in;
   p.trace = dbg_get_gemm_trace();
+#ifdef RF_DEV_HOOKS
   {
     static const int skip = getenv("RF_DBG_GEMM_SKIP") ? atoi(getenv("RF_DBG_GEMM_SKIP")) : 0;
     p.dbg_skip = skip;
   }
+#endif
   if (int rc = set_attr2<EPI, BN>()) return rc;
   static const char* kNames[4] = {"gemm_bias", "gemm_gelu", "gemm_gate_res", "gemm_qkv_rms_rope"};
   const char* name = p.g[0].conv_w ? (EPI == EPI_GATE_RES ? "conv_res" : "conv_bias") : kNames[EPI];
@@ -570,10 +580,12 @@ int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups
   // (28 MB) survives between bands; measured DRAM reads per launch, band 12 -> 4 (ncu, B200):
   // MLP-in 176 -> 112 MB (operands: 104 MB), N = 9216 133 -> 88 MB (85 MB).  Same run time.
   p.band = p.n_tiles <= 12 ? p.n_tiles : 4;
+#ifdef RF_DEV_HOOKS
   {
-    static const int band_env = getenv("RF_GEMM_BAND") ? atoi(getenv("RF_GEMM_BAND")) : 0;  // dev-only raster experiments
+    static const int band_env = getenv("RF_GEMM_BAND") ? atoi(getenv("RF_GEMM_BAND")) : 0;  // raster experiments
     if (band_env > 0 && band_env < p.n_tiles) p.band = band_env;
   }
+#endif
   int tiles = 0;
   double rows = 0;
   for (int g = 0; g < ngroups; ++g) {
