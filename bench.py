@@ -298,6 +298,33 @@ def main():
     h2d = (lat_host.numel() + txt_host.numel() + pool_host.numel()) * 2
     d2h = res.numel() * 2 + 8
 
+    # ---- e2e at the reference's PER-STEP call granularity (tranformer_forward, transformer.py:47):
+    # every step copies its latents host->device from pinned memory and reads the prediction back
+    from reflectionflow_b200.transformer import tranformer_forward
+    t_k16 = t_k.to(torch.bfloat16)
+    gd = torch.tensor([3.5], device=dev)
+    txt_d, pool_d = txt_host.to(dev), pool_host.to(dev)
+    pred_host = torch.empty(1, N_IMG, 64, dtype=torch.bfloat16).pin_memory()
+
+    def step_call(i):
+        x = lat_host.to(dev, non_blocking=True)
+        out = tranformer_forward(model, None, None, None, {}, 0, hidden_states=x, encoder_hidden_states=txt_d,
+                                 pooled_projections=pool_d, timestep=t_k16[i:i + 1].to(dev), img_ids=img_ids,
+                                 txt_ids=txt_ids, guidance=gd, return_dict=False)[0]
+        pred_host.copy_(out, non_blocking=True)
+    step_call(0)
+    barrier()
+    e0.record()
+    for i in range(K):
+        step_call(i)
+    e1.record()
+    barrier()
+    ms_fwd = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_fwd], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_fwd = t.item()
+
     # ---- VAE decode of the final latent (the per-image tail: generate.py:302-307), device-timed
     for _ in range(2):
         pipe.vae.decode_packed(final, H, W, "u8")
@@ -392,6 +419,11 @@ def main():
                     "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "api": "B200FluxPipeline.__call__(prompt_embeds=<pinned host>, latents=<pinned host>, "
                            "output_type='latent') -> score -> .cpu()",
+                    "per_step_forward_api": {"value": args.gpus * K / (ms_fwd / 1e3), "unit": "denoise-steps/s",
+                                             "h2d_bytes_per_step": lat_host.numel() * 2 + 2,
+                                             "d2h_bytes_per_step": lat_host.numel() * 2,
+                                             "api": "tranformer_forward(hidden_states=<pinned host>.to(dev)) -> "
+                                                    "pinned host, once per step (no CUDA graph)"},
                     "note": "same work as `value` plus the copies; the copies are < 1 MB per K-step call, so "
                             "e2e ~= value within run-to-run clock noise (the GPU is power-capped)"},
             "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "clocks": clocks}
