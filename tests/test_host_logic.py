@@ -174,3 +174,49 @@ def test_byte_tokenizer_shapes_and_eos():
     t5 = ByteTokenizer(32128, eos=1, pad=0)
     ids = t5(["hello"], 512)
     assert ids.shape == (1, 512) and ids[0, 5] == 1 and (ids[0, 6:] == 0).all()
+
+
+def test_artefact_saver_orders_writes_per_path_and_flushes(tmp_path):
+    """tts.reflectionflow: artefact writes run on a thread pool; two writes to the same path keep their
+    submission order, flush_saves() joins everything and re-raises a failed write."""
+    import time
+    from reflectionflow_b200.tts import reflectionflow as RF
+    p = str(tmp_path / "a.bin")
+    order = []
+
+    def slow():
+        time.sleep(0.2)
+        order.append("first")
+        open(p, "wb").write(b"first")
+
+    def fast():
+        order.append("second")
+        open(p, "wb").write(b"second")
+    RF._submit_save(p, slow)
+    RF._submit_save(p, fast)
+    for i in range(16):  # other paths run concurrently
+        q = str(tmp_path / f"f{i}.bin")
+        RF._submit_save(q, lambda q=q: open(q, "wb").write(b"x"))
+    RF.flush_saves()
+    assert order == ["first", "second"] and open(p, "rb").read() == b"second"
+    assert len(os.listdir(tmp_path)) == 17
+
+    def boom():
+        raise OSError("disk full")
+    RF._submit_save(str(tmp_path / "bad"), boom)
+    with pytest.raises(OSError):
+        RF.flush_saves()
+    RF.flush_saves()  # the failed future was consumed
+
+
+def test_candidate_png_is_encoded_once():
+    import numpy as np
+    from PIL import Image
+    from reflectionflow_b200.tts.verifiers import Candidate
+    img = Image.fromarray((np.arange(64 * 64 * 3) % 251).astype("uint8").reshape(64, 64, 3))
+    c = Candidate("x/1_round@7.png", 7, image=img)
+    b1 = c.png_bytes()
+    assert b1 is c.png_bytes() and b1[:8] == b"\x89PNG\r\n\x1a\n"
+    import io
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(b1))), np.asarray(img))
+    assert Candidate("y", 0).png_bytes() is None
