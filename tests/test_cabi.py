@@ -70,3 +70,40 @@ def test_no_gpu_fails_loudly_vae_and_text():
     h = ctypes.c_void_p()
     assert lib.rf_text_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
     assert b"no CUDA device" in lib.rf_last_error()
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not on PATH")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = str(tmp_path / "c_abi_linear")
+    libdir = os.path.join(ROOT, "reflectionflow_b200")
+    cmd = ["gcc", "-std=c11", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(cuda, "include"), os.path.join(ROOT, "examples", "c_abi_linear.c"),
+           "-L" + libdir, "-lrf_b200", "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+           "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_c_example_builds_against_the_header_and_fails_loudly_without_gpu(tmp_path):
+    """include/rf_b200.h is plain C11 and the library links from C (no Python, no torch)."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_linear_matches_scalar_host_loop(tmp_path):
+    """rf_op_linear driven from plain C agrees with a scalar host loop (<= 1 bf16 ulp on < 2 % of outputs)."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "c_abi_linear: OK" in r.stdout
