@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RF_B200_ABI_VERSION 1
+#define RF_B200_ABI_VERSION 2
 
 /* error / version ------------------------------------------------------------------------- */
 const char* rf_last_error(void);
@@ -120,11 +120,12 @@ int rf_dit_load_weight(rf_dit* h, const char* key, const void* src, int64_t nume
 
 /* peft LoRA factors of one target Linear (pipe.load_lora_weights, tts_reflectionflow.py:503-505;
  * target list train_flux/config.yaml:53).  module = diffusers module path without ".weight"
- * (e.g. "single_transformer_blocks.0.proj_out"); A: [r, in] bf16, B: [out, r] bf16 (device);
- * scale = lora_alpha / r.  Applied to condition tokens only unless latent_lora is set in
- * rf_dit_prepare (lora_controller.py:5-42). */
+ * (e.g. "single_transformer_blocks.0.proj_out"); A: [r, in_features] bf16, B: [out_features, r]
+ * bf16 (device); in_/out_features are checked against the target Linear (a mismatched adapter
+ * file is an error, not an out-of-bounds read); scale = lora_alpha / r.  Applied to condition
+ * tokens only unless latent_lora is set in rf_dit_prepare (lora_controller.py:5-42). */
 int rf_dit_set_lora(rf_dit* h, const char* module, const void* A, const void* B, int r,
-                    float scale);
+                    int in_features, int out_features, float scale);
 
 /* Number of parameters still missing (0 = ready); names via rf_last_error(). */
 int rf_dit_missing_weights(rf_dit* h);

@@ -79,7 +79,7 @@ def _declare(lib):
         lib.rf_dit_load_weight.restype = ci
         lib.rf_dit_load_weight.argtypes = [vp, c_char_p, vp, c_int64]
         lib.rf_dit_set_lora.restype = ci
-        lib.rf_dit_set_lora.argtypes = [vp, c_char_p, vp, vp, ci, cf]
+        lib.rf_dit_set_lora.argtypes = [vp, c_char_p, vp, vp, ci, ci, ci, cf]
         lib.rf_dit_missing_weights.restype = ci
         lib.rf_dit_missing_weights.argtypes = [vp]
         lib.rf_dit_prepare.restype = ci

@@ -164,6 +164,9 @@ void new_lora(rf_dit* h, Arena& ar, const std::string& mod, LoraT& t, int out, i
   t.out = out;
   t.A = A_view ? A_view : ar.take(static_cast<int64_t>(kLoraPad) * in);
   t.B = ar.take(static_cast<int64_t>(out) * kLoraPad);
+  // unset targets must contribute exactly zero (a q-only adapter still runs the stacked q|k|v path)
+  if (t.A) cudaMemset(t.A, 0, static_cast<size_t>(kLoraPad) * in * 2);
+  if (t.B) cudaMemset(t.B, 0, static_cast<size_t>(out) * kLoraPad * 2);
   h->lora_slots[mod] = &t;
 }
 
@@ -370,16 +373,18 @@ int merge_one(rf_dit* h, const LoraT& t, const bf16* W, bf16** Wm, int rows_off,
     void* p = nullptr;
     if (dev_alloc(h, &p, static_cast<size_t>(out_total) * t.in * 2)) return -2;
     *Wm = static_cast<bf16*>(p);
-    RF_CHECK_CUDA(cudaMemcpyAsync(*Wm, W, static_cast<size_t>(out_total) * t.in * 2,
-                                  cudaMemcpyDeviceToDevice, s));
   }
-  if (!t.set) return 0;
   const size_t off = static_cast<size_t>(rows_off) * t.in;
+  if (!t.set) {  // no adapter on this target: the merged copy is the (possibly reloaded) base weight
+    RF_CHECK_CUDA(cudaMemcpyAsync(*Wm + off, W + off, static_cast<size_t>(t.out) * t.in * 2,
+                                  cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
   return rf::lora_merge_launch(W + off, t.A, t.B, *Wm + off, t.out, t.in, kLoraPad, s);
 }
 int merge_all(rf_dit* h, cudaStream_t s) {
   const int D = h->D;
-  if (h->l_x_emb.set || true) RF_TRY(merge_one(h, h->l_x_emb, h->x_emb.w, &h->x_emb_m, 0, D, s));
+  RF_TRY(merge_one(h, h->l_x_emb, h->x_emb.w, &h->x_emb_m, 0, D, s));
   for (auto& b : h->dbl) {
     RF_TRY(merge_one(h, b.l_q, b.qkv.w, &b.qkv_m, 0, 3 * D, s));
     RF_TRY(merge_one(h, b.l_k, b.qkv.w, &b.qkv_m, D, 3 * D, s));
@@ -481,7 +486,7 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       g[2].rope_cos = h->crope_cos; g[2].rope_sin = h->crope_sin;
       if (h->use_merged) {
         g[2].W = b.qkv_m;
-      } else if (b.l_q.set) {
+      } else if (b.l_q.set || b.l_k.set || b.l_v.set) {
         RF_TRY(lora_term_qkv(h, b.qkvA, b.l_q, b.l_k, b.l_v, g[2].A, D, S_cond.rows, h->LL, D3, s));
         g[2].addend = h->LL; g[2].ldadd = D3;
       }
@@ -577,7 +582,7 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       g[1].rope_cos = h->crope_cos; g[1].rope_sin = h->crope_sin;
       if (h->use_merged) {
         g[1].W = b.qkv_m;
-      } else if (b.l_q.set) {
+      } else if (b.l_q.set || b.l_k.set || b.l_v.set) {
         RF_TRY(lora_term_qkv(h, b.qkvA, b.l_q, b.l_k, b.l_v, g[1].A, D, S_cond.rows, h->LL, D3, s));
         g[1].addend = h->LL; g[1].ldadd = D3;
       }
@@ -783,11 +788,12 @@ int rf_dit_load_weight(rf_dit* h, const char* key, const void* src, int64_t nume
   RF_CHECK_CUDA(cudaMemcpy(it->second.dst, src, static_cast<size_t>(numel) * 2,
                            cudaMemcpyDeviceToDevice));
   it->second.loaded = true;
+  h->lora_merged = false;  // merged W + BA copies (fuse_lora mode) are stale now
   return 0;
 }
 
 int rf_dit_set_lora(rf_dit* h, const char* module, const void* A, const void* B, int r,
-                    float scale) {
+                    int in_features, int out_features, float scale) {
   if (!h || !module || !A || !B) {
     rf::set_error("rf_dit_set_lora: null argument");
     return -1;
@@ -806,6 +812,12 @@ int rf_dit_set_lora(rf_dit* h, const char* module, const void* A, const void* B,
     return -1;
   }
   LoraT& t = *it->second;
+  if (in_features != t.in || out_features != t.out) {
+    rf::set_error(std::string("rf_dit_set_lora: ") + module + " expects A [r, " + std::to_string(t.in) +
+                  "], B [" + std::to_string(t.out) + ", r]; got in=" + std::to_string(in_features) +
+                  " out=" + std::to_string(out_features));
+    return -4;
+  }
   RF_CHECK_CUDA(cudaMemset(t.A, 0, static_cast<size_t>(kLoraPad) * t.in * 2));
   RF_CHECK_CUDA(cudaMemset(t.B, 0, static_cast<size_t>(t.out) * kLoraPad * 2));
   RF_CHECK_CUDA(cudaMemcpy(t.A, A, static_cast<size_t>(r) * t.in * 2, cudaMemcpyDeviceToDevice));
@@ -814,6 +826,7 @@ int rf_dit_set_lora(rf_dit* h, const char* module, const void* A, const void* B,
   t.set = true;
   h->any_lora = true;
   h->lora_merged = false;
+  drop_graph(h);  // the captured step may predate this adapter (different launch list)
   return 0;
 }
 
@@ -944,7 +957,7 @@ int rf_dit_prepare(rf_dit* h, int batch, int n_txt, int n_img, int n_cond, const
   return 0;
 }
 
-static int check_ready(rf_dit* h, const char* who) {
+static int check_ready(rf_dit* h, const char* who, cudaStream_t s) {
   if (!h) {
     rf::set_error(std::string(who) + ": null handle");
     return -1;
@@ -954,13 +967,19 @@ static int check_ready(rf_dit* h, const char* who) {
     return -1;
   }
   if (rf_dit_missing_weights(h) != 0) return -4;
+  // fuse_lora mode: weights or adapters changed since the last merge -> re-merge before use
+  h->use_merged = (h->flags & 8) != 0 && h->any_lora && h->n_cond > 0;
+  if (h->use_merged && !h->lora_merged) {
+    drop_graph(h);
+    RF_TRY(merge_all(h, s));
+  }
   return 0;
 }
 
 int rf_dit_forward(rf_dit* h, const void* latents, const void* txt, const void* pooled,
                    const void* timestep, const float* guidance, const void* cond_latents,
                    void* out, void* stream) {
-  int rc = check_ready(h, "rf_dit_forward");
+  int rc = check_ready(h, "rf_dit_forward", static_cast<cudaStream_t>(stream));
   if (rc) return rc;
   if (!latents || !txt || !pooled || !timestep || !out || (h->n_cond > 0 && !cond_latents) ||
       (h->cfg.guidance_embeds && !guidance)) {
@@ -991,7 +1010,7 @@ int rf_dit_forward(rf_dit* h, const void* latents, const void* txt, const void* 
 int rf_dit_denoise(rf_dit* h, void* latents_inout, const void* txt, const void* pooled,
                    const uint16_t* timesteps_bf16_host, const float* sigmas_host, int n_steps,
                    float guidance_scale, const void* cond_latents, void* stream) {
-  int rc = check_ready(h, "rf_dit_denoise");
+  int rc = check_ready(h, "rf_dit_denoise", static_cast<cudaStream_t>(stream));
   if (rc) return rc;
   if (!latents_inout || !txt || !pooled || !timesteps_bf16_host || !sigmas_host || n_steps <= 0 ||
       (h->n_cond > 0 && !cond_latents)) {

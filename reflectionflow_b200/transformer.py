@@ -92,6 +92,7 @@ class B200FluxTransformer2DModel:
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
         """`sd` uses diffusers' FluxTransformer2DModel keys.  Tensors may live anywhere; each is
         staged to the device in bf16 and copied into the handle's packed storage."""
+        self._geom_key = None
         with torch.cuda.device(self.device):
             for k, v in sd.items():
                 if ".lora_" in k:
@@ -174,7 +175,7 @@ class B200FluxTransformer2DModel:
             if mode not in ("exact", "merged"):
                 raise ValueError("lora mode must be 'exact' or 'merged'")
             self.lora_mode = mode
-            self._geom_key = None
+        self._geom_key = None  # adapters changed: rf_dit_prepare must re-run (merged copies, graph)
         pairs = {}
         if lora and all(isinstance(v, (tuple, list)) for v in lora.values()):
             pairs = dict(lora)
@@ -190,9 +191,13 @@ class B200FluxTransformer2DModel:
         with torch.cuda.device(self.device):
             for mod, (A, B) in pairs.items():
                 r = A.shape[0]
+                if A.ndim != 2 or B.ndim != 2 or B.shape[1] != r:
+                    raise ValueError(f"LoRA factors of {mod}: A {tuple(A.shape)} / B {tuple(B.shape)} "
+                                     "are not [r, in] / [out, r]")
                 scale = 1.0 if alpha is None else float(alpha) / r
                 a, b = _bf16c(A, self.device), _bf16c(B, self.device)
                 L.check(self._lib.rf_dit_set_lora(self._h, mod.encode(), L.ptr(a), L.ptr(b), r,
+                                                  int(A.shape[1]), int(B.shape[0]),
                                                   ctypes.c_float(scale)), f"rf_dit_set_lora({mod})")
             torch.cuda.synchronize(self.device)
         return self

@@ -75,6 +75,15 @@ class DistCtx:
         dist.broadcast_object_list(box, src=src, device=self.device if self.device.type == "cuda" else None)
         return box[0]
 
+    def gather_objects(self, local: Any) -> List[Any]:
+        """every rank's (small, picklable) object, in rank order, on every rank"""
+        if self.world == 1:
+            return [local]
+        import torch.distributed as dist
+        out = [None] * self.world
+        dist.all_gather_object(out, local)
+        return out
+
     def barrier(self):
         if self.world > 1:
             import torch.distributed as dist

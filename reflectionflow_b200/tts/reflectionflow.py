@@ -12,8 +12,8 @@ What changes, and why:
     samples the VAE posterior, B.4);
   * images cross rounds in HBM, not as PNG files re-opened from disk: with a VAE attached the
     parent -> condition step is decode -> PIL-exact BICUBIC resize -> encode, all on the device
-    (PNGs are still written for downstream tools); without a VAE the 512x512 condition is formed in
-    latent space (area average of the parent's latent grid) — a labelled stand-in.
+    (PNGs are still written for downstream tools); a pipeline without a VAE cannot form the
+    condition and raises.
 Artefact layout and names (midimg/<round>_round@<seed>.png, best_img_meta.jsonl,
 best_img_detailedscore.jsonl, samples_best/, samples_lastround/, samples_path_bestround/) follow the
 reference so downstream tools keep working."""
@@ -38,23 +38,25 @@ MAX_RETRIES = 5
 RETRY_DELAY = 2
 
 
-def parent_condition_latents(parent_latents: torch.Tensor, height: int, width: int,
-                             condition_size: int) -> torch.Tensor:
-    """[1, (h/16)(w/16), 64] final latent of the parent -> packed [1, (c/16)^2, 64] condition tokens.
-    Stand-in for `vae.decode -> resize(condition_size) -> vae.encode` (tts_reflectionflow.py:273-279,
-    pipeline_tools.py:7-30) until the VAE is native: area-average the latent grid."""
-    b, n, c = parent_latents.shape
-    h, w = 2 * (height // 16), 2 * (width // 16)
-    x = parent_latents.float().view(b, h // 2, w // 2, c // 4, 2, 2).permute(0, 3, 1, 4, 2, 5)
-    x = x.reshape(b, c // 4, h, w)
-    ch = cw = condition_size // 8
-    x = torch.nn.functional.adaptive_avg_pool2d(x, (ch, cw))
-    x = x.view(b, c // 4, ch // 2, 2, cw // 2, 2).permute(0, 2, 4, 1, 3, 5)
-    return x.reshape(b, (ch // 2) * (cw // 2), c).to(parent_latents.dtype)
-
-
 _SAVER = None
 _PENDING: Dict[str, "object"] = {}
+# every candidate of the current prompt's tree by name (the reference re-opens PNGs from disk when it
+# copies a best image of an EARLIER round, tts_reflectionflow.py:408-446; we keep the packed latents,
+# 0.5 MB each, and re-decode on demand)
+_REGISTRY: Dict[str, Dict[str, Candidate]] = {}
+
+
+def _registry(root_dir: str, search_round: int) -> Dict[str, Candidate]:
+    if search_round == 1:
+        _REGISTRY.clear()  # one prompt's tree at a time
+    return _REGISTRY.setdefault(root_dir, {})
+
+
+def _slim(cand: Candidate):
+    """Drop the pixel copies of a candidate that left the active window (latents stay)."""
+    cand.image_u8 = None
+    cand.image = None
+    cand.__dict__.pop("_png", None)
 
 
 def _submit_save(path: str, job: Callable[[], None]):
@@ -106,12 +108,12 @@ def _ensure_pixels(pipe, cand: Candidate, height: int, width: int):
 def parent_condition(pipe, parent: Candidate, height: int, width: int, cond_size: int, seed: int):
     """tts_reflectionflow.py:273-279: the parent IMAGE, resized to condition_size, becomes the `cot`
     condition.  With a VAE attached this is the real path, all on the device: decode -> PIL-exact
-    BICUBIC resize -> encode (posterior noise seeded by the candidate's seed).  Without one, a
-    latent-space area average stands in (labelled in the module docstring)."""
+    BICUBIC resize -> encode (posterior noise seeded by the candidate's seed).  There is no
+    latent-space stand-in: without a VAE the condition cannot be formed."""
     position_delta = [0, -cond_size // 16]
     if getattr(pipe, "vae", None) is None:
-        return Condition("cot", latents=parent_condition_latents(parent.latents, height, width, cond_size),
-                         position_delta=position_delta)
+        raise RuntimeError("the reflection loop needs pipe.vae (decode -> resize -> encode of the parent "
+                           "image, tts_reflectionflow.py:273-279); build the pipeline with with_vae=True")
     from ..resize import resize_u8
     u8 = _ensure_pixels(pipe, parent, height, width)
     small = resize_u8(u8[None], cond_size, cond_size)
@@ -126,7 +128,8 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
            sample_path_lastround: str, sample_path_best: str, sample_path_bestround: str,
            imagetoupdate: List[Candidate], midimg_path: str, total_rounds: int, chains: dict,
            tag: Optional[str] = None, *, verifier=None, reflector=None, ctx: Optional[DistCtx] = None,
-           generate_fn: Callable = _generate, defer_saves: bool = False) -> dict:
+           generate_fn: Callable = _generate, defer_saves: bool = False,
+           condition_fn: Optional[Callable] = None) -> dict:
     """`defer_saves=True` leaves artefact writes in flight when the round returns (they overlap the
     next round; the caller ends with `flush_saves()`); by default the round's files are on disk."""
     ctx = ctx or DistCtx()
@@ -146,7 +149,11 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
     t0 = time.time()
     n_prev = len(imagetoupdate)
     mine = ctx.my_candidates(n_prev)
-    local_out = verifier.score([imagetoupdate[i] for i in mine], [original_prompt] * len(mine))
+    if getattr(verifier, "needs_images", False):  # real verifiers look at pixels: decode the parents
+        for i in mine:
+            _ensure_pixels(pipe, imagetoupdate[i], pa["height"], pa["width"])
+            imagetoupdate[i].pil()
+    local_out = verifier.score([imagetoupdate[i] for i in mine], [original_prompt] * len(mine), tag=tag)
     outputs = _exchange_outputs(ctx, verifier_name, choice_of_metric, imagetoupdate, mine, local_out)
     sorted_list = S.sort_outputs(outputs, verifier_name, choice_of_metric)
     if rank0:
@@ -165,31 +172,28 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
     evaluations = [json.dumps(o) for o in selected_outputs]
     if reflection_args and reflection_args.get("run_reflection", False):
         t0 = time.time()
-        if rank0:
+        def reflect():
             retries = 0
             while True:
                 try:
-                    update_reflections = reflector.generate_reflections(
+                    return reflector.generate_reflections(
                         selected, original_prompt, updated_prompt, reflections, evaluations)
-                    break
                 except Exception as e:  # tts_reflectionflow.py:208-219
                     retries += 1
                     if retries >= MAX_RETRIES:
                         raise
                     print(f"Error generating reflection: {e}. Retrying in {RETRY_DELAY} seconds...")
                     time.sleep(RETRY_DELAY)
-        update_reflections = ctx.broadcast_object(update_reflections)
+        update_reflections = _rank0_call(ctx, reflect)
         reflection_performed = True
         if rank0:
             print(f"Time taken for reflection generation: {time.time() - t0} seconds")
     prompt_refiner_args = config_cp.get("prompt_refiner_args", None)
     if prompt_refiner_args and prompt_refiner_args.get("run_refinement", False):
         t0 = time.time()
-        if rank0:
-            refined_prompt = reflector.refine_prompt(
-                selected, original_prompt, updated_prompt, update_reflections,
-                evaluations if verifier_name == "openai" else None)
-        refined_prompt = ctx.broadcast_object(refined_prompt)
+        refined_prompt = _rank0_call(ctx, lambda: reflector.refine_prompt(
+            selected, original_prompt, updated_prompt, update_reflections,
+            evaluations if verifier_name == "openai" else None))
         refinement_performed = True
         if rank0:
             print(f"Time taken for prompt refinement: {time.time() - t0} seconds")
@@ -217,7 +221,7 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
     for i in ctx.my_candidates(num_samples):
         seed, noise = noise_items[i]
         parent = selected[i]
-        cond = parent_condition(pipe, parent, pa["height"], pa["width"], cond_size, seed)
+        cond = (condition_fn or parent_condition)(pipe, parent, pa["height"], pa["width"], cond_size, seed)
         result = generate_fn(pipe, prompt=[prompts[i]], conditions=[cond], height=pa["height"],
                              width=pa["width"], model_config=config.get("model", None),
                              default_lora=True, latents=noise, output_type="latent")
@@ -237,7 +241,10 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
         _save_candidate(new_cands[i], full_imgnames[i])
     t0 = time.time()
     mine = ctx.my_candidates(num_samples)
-    local_out = verifier.score([new_cands[i] for i in mine], [original_prompt] * len(mine))
+    if getattr(verifier, "needs_images", False):
+        for i in mine:
+            new_cands[i].pil()
+    local_out = verifier.score([new_cands[i] for i in mine], [original_prompt] * len(mine), tag=tag)
     outputs = _exchange_outputs(ctx, verifier_name, choice_of_metric, new_cands, mine, local_out)
     if rank0:
         print(f"Time taken for evaluation: {time.time() - t0} seconds")
@@ -245,7 +252,17 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
     # ---- 9. chains / best-of bookkeeping (identical on every rank; files from rank 0)
     S.update_chains(chains, search_round, full_imgnames, outputs, selected_imgs, verifier_name,
                     choice_of_metric)
-    by_name = {c.name: c for c in list(imagetoupdate) + new_cands}
+    by_name = _registry(root_dir, search_round)
+    active = {c.name for c in list(imagetoupdate) + new_cands}
+    for c in list(imagetoupdate) + new_cands:
+        by_name[c.name] = c
+
+    def materialise(name: str) -> Candidate:
+        if name not in by_name:
+            raise RuntimeError(f"best candidate {name} of an earlier round is not in the registry")
+        c = by_name[name]
+        _ensure_pixels(pipe, c, pa["height"], pa["width"])
+        return c
     if rank0:
         if search_round == total_rounds:
             for i, c in enumerate(new_cands):
@@ -255,13 +272,14 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
                 _save_candidate(c, os.path.join(sample_path_bestround, f"{i:05}.png"))
         else:
             for i, name in enumerate(S.best_per_chain(chains, verifier_name)):
-                if name in by_name:
-                    _save_candidate(by_name[name], os.path.join(sample_path_bestround, f"{i:05}.png"))
+                _save_candidate(materialise(name), os.path.join(sample_path_bestround, f"{i:05}.png"))
         if search_round == total_rounds:
             best = S.global_best(chains, verifier_name)
-            if best in by_name:
-                # the reference names this file with a leaked loop index (App. B.9); we use 00000
-                _save_candidate(by_name[best], os.path.join(sample_path_best, f"{0:05}.png"))
+            # the reference names this file with a leaked loop index (App. B.9); we use 00000
+            _save_candidate(materialise(best), os.path.join(sample_path_best, f"{0:05}.png"))
+    for name, c in by_name.items():  # older rounds keep latents only
+        if name not in active:
+            _slim(c)
 
     datapoint = {"original_prompt": original_prompt, "search_round": search_round,
                  "num_noises": len(noises), "choice_of_metric": choice_of_metric,
@@ -277,10 +295,28 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
     return datapoint
 
 
+def _rank0_call(ctx: DistCtx, fn: Callable):
+    """Run an LLM hook on rank 0 and give every rank its result; a failure on rank 0 is broadcast
+    too, so all ranks raise together instead of hanging in the collective."""
+    box = None
+    if ctx.rank == 0:
+        try:
+            box = ("ok", fn())
+        except Exception as e:  # noqa: BLE001 - re-raised on every rank below
+            box = ("err", f"{type(e).__name__}: {e}")
+    box = ctx.broadcast_object(box)
+    if box[0] == "err":
+        raise RuntimeError(f"rank-0 hook failed: {box[1]}")
+    return box[1]
+
+
 def _exchange_outputs(ctx: DistCtx, verifier_name: str, metric: str, cands: List[Candidate],
                       mine: List[int], local_out: List[dict]) -> List[dict]:
-    """All-gather fixed-size (cand_id, seed, label, score) records and rebuild the reference-shaped
-    output dicts in candidate order on every rank."""
+    """All-gather fixed-size (cand_id, seed, label, score) records — the selection key, identical
+    on every rank — and rebuild the reference-shaped output dicts in candidate order.  The nvila
+    dict is exactly its record; richer verifier outputs (every aspect + explanation of the
+    OpenAI-shaped JSON, which feeds generate_reflections / refine_prompt and
+    best_img_detailedscore.jsonl, tts_reflectionflow.py:184-257) travel whole, as objects."""
     recs = []
     for i, o in zip(mine, local_out):
         if verifier_name == "nvila":
@@ -288,13 +324,20 @@ def _exchange_outputs(ctx: DistCtx, verifier_name: str, metric: str, cands: List
         else:
             recs.append((i, cands[i].seed, 1, float(S.metric_value(o, metric))))
     allr = ctx.gather_records(recs, len(cands))
+    full = {}
+    if verifier_name != "nvila":
+        for part in ctx.gather_objects([(i, o) for i, o in zip(mine, local_out)]):
+            full.update(dict(part))
     outs = []
     for cid, seed, label, score in allr:
         if verifier_name == "nvila":
             outs.append({"image_name": cands[cid].name, "label": "yes" if label else "no", "score": score})
         else:
-            sc = int(score) if float(score).is_integer() else score
-            outs.append({metric: {"score": sc, "explanation": ""}, "image_name": cands[cid].name})
+            o = dict(full[cid])
+            if float(S.metric_value(o, metric)) != float(score):
+                raise RuntimeError(f"candidate {cid}: score record and verifier output disagree")
+            o.setdefault("image_name", cands[cid].name)
+            outs.append(o)
     return outs
 
 

@@ -78,8 +78,11 @@ def nvila_key(output: dict):
     return (0, -output["score"]) if output["label"] == "yes" else (1, output["score"])
 
 
+METRIC_VERIFIERS = ("openai", "ours")  # ordered by outputs[choice_of_metric] (descending)
+
+
 def sort_outputs(outputs: List[dict], verifier_name: str, choice_of_metric: str = None) -> List[dict]:
-    if verifier_name == "openai":
+    if verifier_name in METRIC_VERIFIERS:
         return sorted(outputs, key=lambda x: metric_value(x, choice_of_metric), reverse=True)
     if verifier_name == "nvila":
         return sorted(outputs, key=nvila_key)
@@ -113,16 +116,17 @@ def update_chains(chains: Dict[str, dict], search_round: int, full_names: List[s
                   choice_of_metric: str = None) -> Dict[str, dict]:
     """tts_reflectionflow.py:359-396, including the asymmetry that the nvila branch stops at the
     first chain containing the parent while the openai branch updates every such chain."""
-    if verifier_name not in ("openai", "nvila"):
+    if verifier_name not in METRIC_VERIFIERS + ("nvila",):
         raise NotImplementedError(f"Verifier {verifier_name} not supported")
+    metric = verifier_name in METRIC_VERIFIERS
     if search_round == 1:
         for i, name in enumerate(full_names):
             if name not in chains:
-                chains[name] = {"images": [], "scores": []} if verifier_name == "openai" \
+                chains[name] = {"images": [], "scores": []} if metric \
                     else {"images": [], "scores": [], "labels": []}
             chains[name]["images"].append(name)
-            if verifier_name == "openai":
-                chains[name]["scores"].append(outputs[i][choice_of_metric]["score"])
+            if metric:
+                chains[name]["scores"].append(metric_value(outputs[i], choice_of_metric))
             else:
                 chains[name]["labels"].append(outputs[i]["label"])
                 chains[name]["scores"].append(outputs[i]["score"])
@@ -132,8 +136,8 @@ def update_chains(chains: Dict[str, dict], search_round: int, full_names: List[s
         for key in chains:
             if parent in chains[key]["images"]:
                 chains[key]["images"].append(name)
-                if verifier_name == "openai":
-                    chains[key]["scores"].append(outputs[i][choice_of_metric]["score"])
+                if metric:
+                    chains[key]["scores"].append(metric_value(outputs[i], choice_of_metric))
                 else:
                     chains[key]["labels"].append(outputs[i]["label"])
                     chains[key]["scores"].append(outputs[i]["score"])
@@ -145,7 +149,7 @@ def best_per_chain(chains: Dict[str, dict], verifier_name: str) -> List[str]:
     """tts_reflectionflow.py:408-421."""
     best = []
     for chain in chains.values():
-        if verifier_name == "openai":
+        if verifier_name in METRIC_VERIFIERS:
             scores = chain["scores"]
             idx = max(range(len(scores)), key=lambda j: (scores[j], -j))  # np.argmax: first max
         else:
@@ -159,7 +163,7 @@ def best_per_chain(chains: Dict[str, dict], verifier_name: str) -> List[str]:
 
 def global_best(chains: Dict[str, dict], verifier_name: str) -> str:
     """tts_reflectionflow.py:428-446."""
-    if verifier_name == "openai":
+    if verifier_name in METRIC_VERIFIERS:
         allv = [(s, n) for c in chains.values() for n, s in zip(c["images"], c["scores"])]
         return sorted(allv, key=lambda x: x[0], reverse=True)[0][1]
     allv = [(l, s, n) for c in chains.values()

@@ -64,8 +64,10 @@ class StubVerifier:
     openai: {<aspect>: {"score": int 0-10, "explanation": str}, ..., "overall_score": {...}}
             (verifiers/openai_verifier.py:23-69) — `choice_of_metric` indexes it."""
 
+    needs_images = False
+
     def __init__(self, name: str = "nvila", choice_of_metric: str = "overall_score"):
-        assert name in ("nvila", "openai")
+        assert name in ("nvila", "openai", "ours")
         self.name = name
         self.choice_of_metric = choice_of_metric
 
@@ -81,40 +83,182 @@ class StubVerifier:
             if p_yes >= 0.5:
                 return {"image_name": cand.name, "label": "yes", "score": p_yes}
             return {"image_name": cand.name, "label": "no", "score": 1.0 - p_yes}
+        if self.name == "ours":  # scalar reward under choice_of_metric (ImageVerifierOurs shape)
+            return {self.choice_of_metric: float(v), "VQ": float(v), "image_name": cand.name}
         s = max(0, min(10, int(round(5 + 60.0 * v))))
         return {self.choice_of_metric: {"score": s, "explanation": "stub"},
                 "image_name": cand.name}
 
-    def score(self, cands: Sequence[Candidate], prompts: Sequence[str]) -> List[Dict[str, Any]]:
+    def score(self, cands: Sequence[Candidate], prompts: Sequence[str], tag=None) -> List[Dict[str, Any]]:
         return [self.score_one(c, p) for c, p in zip(cands, prompts)]
 
 
+def _images_of(cands: Sequence[Candidate]):
+    imgs = []
+    for c in cands:
+        im = c.pil()
+        if im is None:
+            raise RuntimeError(f"{c.name}: the verifier needs pixels — decode the candidate first "
+                               "(pipeline built with with_vae=True)")
+        imgs.append(im)
+    return imgs
+
+
 class NvilaVerifier:
-    """Adapter for the real NVILA verifier returned by the reference's load_model():
-    `model.generate_content([PIL, prompt]) -> (label, scores)`; score = scores[0][0, yes|no id]
-    (tts_reflectionflow.py:160-164).  Needs decoded images (VAE) and Hub weights."""
+    """Adapter for the real NVILA verifier returned by the reference's load_model()
+    (verifiers/nvila_verifier.py:4-10): `model.generate_content([PIL, prompt]) -> (label, scores)`;
+    score = scores[0][0, yes_id | no_id] (tts_reflectionflow.py:157-164, 345-352).  Uniform hook:
+    score(candidates, prompts) -> [{"image_name", "label", "score"}], images taken from HBM-decoded
+    candidates instead of re-opened PNGs."""
 
     name = "nvila"
+    needs_images = True
 
     def __init__(self, model, yes_id: int, no_id: int):
         self.model, self.yes_id, self.no_id = model, yes_id, no_id
 
-    def score(self, cands: Sequence[Candidate], prompts: Sequence[str]):
+    def score(self, cands: Sequence[Candidate], prompts: Sequence[str], tag=None):
         out = []
-        for c, p in zip(cands, prompts):
-            if c.image is None:
-                raise RuntimeError("NVILA needs decoded images: attach a VAE to the pipeline")
-            r1, scores1 = self.model.generate_content([c.image, p])
-            tok = self.yes_id if r1 == "yes" else self.no_id
-            out.append({"image_name": c.name, "label": "yes" if r1 == "yes" else "no",
+        for c, im, p in zip(cands, _images_of(cands), prompts):
+            r1, scores1 = self.model.generate_content([im, p])
+            yes = r1 == "yes"
+            tok = self.yes_id if yes else self.no_id
+            out.append({"image_name": c.name, "label": "yes" if yes else "no",
                         "score": scores1[0][0, tok].detach().cpu().float().item()})
         return out
 
 
-def load_verifier(verifier_args: dict, synthetic: bool, choice_of_metric: str = "overall_score"):
-    """tts_reflectionflow.py:515-522: only "openai" and "nvila" are accepted."""
+# ---- response schemas of the OpenAI-shaped verifier (verifiers/openai_verifier.py:23-69): the JSON
+# keys are part of the on-disk format (best_img_detailedscore.jsonl) and of `choice_of_metric`.
+GRADING_ASPECTS = {
+    None: ("accuracy_to_prompt", "creativity_and_originality", "visual_quality_and_realism",
+           "consistency_and_cohesion", "emotional_or_thematic_resonance", "overall_score"),
+    "single_object": ("object_completeness", "detectability", "occlusion_handling", "overall_score"),
+    "two_object": ("separation_clarity", "individual_completeness", "relationship_accuracy", "overall_score"),
+    "counting": ("count_accuracy", "object_uniformity", "spatial_legibility", "overall_score"),
+    "colors": ("color_fidelity", "contrast_effectiveness", "multi_object_consistency", "overall_score"),
+    "position": ("position_accuracy", "occlusion_management", "perspective_consistency", "overall_score"),
+    "color_attr": ("attribute_binding", "contrast_effectiveness", "material_consistency", "overall_score"),
+}
+_GRADING_MODELS: Dict[Any, Any] = {}
+
+
+def grading_model(tag: Optional[str]):
+    """pydantic response_format for a GenEval tag (None = the general rubric)."""
+    if tag not in GRADING_ASPECTS:
+        raise KeyError(f"unknown verifier tag {tag!r}")
+    if tag not in _GRADING_MODELS:
+        from pydantic import BaseModel, create_model
+
+        class Score(BaseModel):
+            score: int
+            explanation: str
+        name = "Grading" if tag is None else f"Grading_{tag}"
+        _GRADING_MODELS[tag] = create_model(name, **{a: (Score, ...) for a in GRADING_ASPECTS[tag]})
+    return _GRADING_MODELS[tag]
+
+
+def _jpeg_data_url(image) -> str:
+    import base64
+    import io
+    if isinstance(image, str):
+        with open(image, "rb") as f:
+            raw = f.read()
+    else:
+        buf = io.BytesIO()
+        image.save(buf, format="JPEG")
+        raw = buf.getvalue()
+    return "data:image/jpeg;base64," + base64.b64encode(raw).decode("utf-8")
+
+
+def _map_in_order(fn, items, max_workers: int = 4):
+    """The reference fans the HTTP calls out over <= 4 threads and appends results in COMPLETION
+    order (openai_verifier.py:153-164), so outputs[i] need not belong to image i; here results keep
+    the input order (a candidate is always scored by its own response)."""
+    if not items:
+        return []
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(items), max_workers)) as ex:
+        return list(ex.map(fn, items))
+
+
+class OpenAIShapedVerifier:
+    """Accept-a-client adapter with the schema of verifiers/openai_verifier.py: any object exposing
+    `client.beta.chat.completions.parse(model=, messages=, temperature=, response_format=)` (the
+    OpenAI SDK, or a local server with the same surface) scores images against the rubric prompts.
+    score(candidates, prompts, tag) -> [{<aspect>: {"score": int, "explanation": str}, ...}]."""
+
+    name = "openai"
+    needs_images = True
+
+    def __init__(self, client, system_instruction, model_name: str = "gpt-4o-2024-11-20",
+                 choice_of_metric: str = "overall_score"):
+        self.client, self.system_instruction = client, system_instruction
+        self.model_name, self.choice_of_metric = model_name, choice_of_metric
+
+    def prepare_inputs(self, images, prompts):
+        images = images if isinstance(images, list) else [images]
+        prompts = prompts if isinstance(prompts, list) else [prompts]
+        return [{"role": "user", "content": [{"type": "text", "text": p},
+                                              {"type": "image_url", "image_url": {"url": _jpeg_data_url(im)}}]}
+                for p, im in zip(prompts, images)]
+
+    def score_inputs(self, inputs, tag=None, **_):
+        instr = self.system_instruction if tag is None else self.system_instruction[tag]
+        system_message = {"role": "system", "content": instr}
+        fmt = grading_model(tag)
+
+        def call(parts):
+            r = self.client.beta.chat.completions.parse(model=self.model_name, messages=[system_message, parts],
+                                                        temperature=1, response_format=fmt)
+            return r.choices[0].message.parsed.model_dump()
+        return _map_in_order(call, list(inputs))
+
+    def score(self, cands: Sequence[Candidate], prompts: Sequence[str], tag=None):
+        outs = self.score_inputs(self.prepare_inputs(_images_of(cands), list(prompts)), tag=tag)
+        for c, o in zip(cands, outs):
+            o["image_name"] = c.name
+        return outs
+
+
+class ImageVerifierOurs:
+    """The "ours" branch the reference's loader lacks (tts_reflectionflow.py:515-522 accepts only
+    openai / nvila): the repo's own Image-Verifier — a Qwen2.5-VL backbone with a scalar `rm_head`
+    (reward_modeling/trainer.py:59-172) driven through reward_modeling/inference.py:155-180's
+    `reward(images, prompts, use_norm) -> [{"VQ": r, "Overall": r}]`.  One batched in-process call per
+    round share; output dicts carry the scalar under `choice_of_metric` ("Overall"), so the
+    metric-ordered selection rules apply unchanged (descending reward)."""
+
+    name = "ours"
+    needs_images = True
+
+    def __init__(self, inferencer, choice_of_metric: str = "Overall", use_norm: bool = True,
+                 batch_size: int = 8):
+        self.inferencer, self.choice_of_metric = inferencer, choice_of_metric
+        self.use_norm, self.batch_size = use_norm, batch_size
+
+    def score(self, cands: Sequence[Candidate], prompts: Sequence[str], tag=None):
+        imgs, out = _images_of(cands), []
+        for o in range(0, len(imgs), self.batch_size):
+            rs = self.inferencer.reward(imgs[o:o + self.batch_size], list(prompts[o:o + self.batch_size]),
+                                        use_norm=self.use_norm)
+            out.extend(rs)
+        res = []
+        for c, r in zip(cands, out):
+            d = {k: float(v) for k, v in r.items()}
+            if self.choice_of_metric not in d:
+                raise KeyError(f"reward model returned {sorted(d)}, not {self.choice_of_metric!r}")
+            d["image_name"] = c.name
+            res.append(d)
+        return res
+
+
+def load_verifier(verifier_args: dict, synthetic: bool, choice_of_metric: str = "overall_score",
+                  client=None, inferencer=None):
+    """tts_reflectionflow.py:515-522 accepts "openai" and "nvila"; "ours" (the Image-Verifier reward
+    model) is the branch SURVEY §8f-3 adds.  `client` / `inferencer` inject the external model."""
     name = verifier_args.get("name", "openai")
-    if name not in ("openai", "nvila"):
+    if name not in ("openai", "nvila", "ours"):
         raise ValueError(f"Verifier {name} not supported")
     if synthetic:
         return StubVerifier(name, choice_of_metric)
@@ -125,7 +269,85 @@ def load_verifier(verifier_args: dict, synthetic: bool, choice_of_metric: str = 
         yes_id = model.tokenizer.encode("yes", add_special_tokens=False)[0]
         no_id = model.tokenizer.encode("no", add_special_tokens=False)[0]
         return NvilaVerifier(model, yes_id, no_id)
-    raise RuntimeError("the OpenAI verifier needs network access; run with --synthetic offline")
+    if name == "ours":
+        if inferencer is None:
+            raise RuntimeError("verifier 'ours' needs the Image-Verifier inferencer (an object with "
+                               ".reward(images, prompts, use_norm)); its checkpoint is not reachable offline")
+        return ImageVerifierOurs(inferencer, choice_of_metric)
+    if client is None:
+        raise RuntimeError("the OpenAI verifier needs a client (network access); run with --synthetic offline")
+    from .utils import load_verifier_prompt
+    return OpenAIShapedVerifier(client, load_verifier_prompt(verifier_args["verifier_prompt_relpath"]),
+                                verifier_args.get("model_name", "gpt-4o-2024-11-20"), choice_of_metric)
+
+
+class OpenAIShapedReflector:
+    """Accept-a-client reflection writer + prompt refiner with the message layout of
+    openai_verifier.py:166-317 (`client.chat.completions.create(model=, messages=, temperature=)`).
+    Same list-in / list-out shapes as StubReflector; results keep the input order."""
+
+    def __init__(self, client, reflexion_instruction: str, refine_instruction: str,
+                 model_name: str = "gpt-4o-2024-11-20"):
+        self.client, self.model_name = client, model_name
+        self.system_message_reflexion = {"role": "system", "content": reflexion_instruction}
+        self.system_message_refine = {"role": "system", "content": refine_instruction}
+
+    def _chat(self, system_message, inputs):
+        def call(parts):
+            r = self.client.chat.completions.create(model=self.model_name, messages=[system_message, parts],
+                                                    temperature=1)
+            return r.choices[0].message.content
+        return _map_in_order(call, list(inputs))
+
+    def prepare_reflexion_prompt_inputs(self, images, original_prompt, current_prompt, reflections, evaluations):
+        inputs = []
+        for im, op, cp, rf, ev in zip(images, original_prompt, current_prompt, reflections, evaluations):
+            inputs.append({"role": "user", "content": [
+                {"type": "text", "text": "Original prompt: " + op},
+                {"type": "text", "text": f"The updated prompt to generate the image is: {cp}[Reflexion]: {rf}"},
+                {"type": "text", "text": f"Evaluation of the generated image: {ev}"},
+                {"type": "text", "text": "Generated images:"},
+                {"type": "image_url", "image_url": {"url": _jpeg_data_url(im)}},
+                {"type": "text", "text": "Please generate instructions following the defined rules."}]})
+        return inputs
+
+    def prepare_refine_prompt_inputs(self, original_prompt, images=None, evaluations=None, current_prompt=None,
+                                     reflections=None):
+        n = len(original_prompt)
+        fill = lambda v: [None] * n if v is None else list(v)[:n]
+        inputs = []
+        for op, im, ev, cp, rf in zip(original_prompt, fill(images), fill(evaluations), fill(current_prompt),
+                                      fill(reflections)):
+            content = [{"type": "text", "text": f"Original prompt: {op}"}]
+            if cp:
+                content.append({"type": "text", "text": f"Current prompt: {cp}"})
+            if rf:
+                content.append({"type": "text", "text": f"Reflection prompt: {rf}"})
+            if im is not None:
+                content.append({"type": "image_url", "image_url": {"url": _jpeg_data_url(im)}})
+            if ev:
+                content.append({"type": "text", "text": f"Evaluation of the generated images: {ev}"})
+            content.append({"type": "text", "text": "Please refine the current prompt to improve the overall "
+                                                    "quality of the future generated images."})
+            inputs.append({"role": "user", "content": content})
+        return inputs
+
+    # ---- the two hooks sample() calls (same signatures as StubReflector)
+    def generate_reflections(self, cands, original_prompt, current_prompts, reflections, evaluations):
+        n = len(cands)
+        inputs = self.prepare_reflexion_prompt_inputs(_images_of(cands), [original_prompt] * n,
+                                                      list(current_prompts), list(reflections), list(evaluations))
+        out = self._chat(self.system_message_reflexion, inputs)
+        if len(out) != n:
+            raise RuntimeError("reflection writer returned a short list")
+        return out
+
+    def refine_prompt(self, cands, original_prompt, current_prompts, reflections, evaluations=None):
+        n = len(cands)
+        inputs = self.prepare_refine_prompt_inputs([original_prompt] * n, images=_images_of(cands),
+                                                   evaluations=evaluations, current_prompt=list(current_prompts),
+                                                   reflections=reflections)
+        return self._chat(self.system_message_refine, inputs)
 
 
 class StubReflector:

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert "rf_dit_forward" in names and "rf_op_linear" in names and len(names) >= 18
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/rf_b200.h but not exported"
-    assert lib.rf_abi_version() == 1
+    assert lib.rf_abi_version() == 2
 
 
 def test_sass_is_blackwell_native():

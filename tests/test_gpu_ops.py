@@ -216,10 +216,12 @@ def test_attention_sharp_rows():
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
-def test_attention_cond_modes(mode):
+@pytest.mark.parametrize("n_tok,n_main,heads", [(640, 512, 2), (5632, 4608, 24)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_attention_cond_modes(mode, n_tok, n_main, heads):
+    """cond-stream key ranges at the small size and at the entry-B headline geometry
+    (512 txt + 4096 img + 1024 cond = 5632 tokens, 24 heads; block.py:97-125)"""
     lib = L.load()
-    n_tok, n_main, heads = 640, 512, 2
     inner = heads * 128
     qkv = _randn(n_tok, 3 * inner, seed=32)
     q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]

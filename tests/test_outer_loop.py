@@ -40,6 +40,21 @@ class FakePipe:
     vae = None
 
 
+def fake_condition(pipe, parent, height, width, cond_size, seed):
+    """test-only stand-in for decode -> resize -> encode (the product path needs the CUDA VAE):
+    area-average of the parent's latent grid."""
+    from reflectionflow_b200.pipeline import Condition
+    lat = parent.latents
+    b, n, c = lat.shape
+    h, w = 2 * (height // 16), 2 * (width // 16)
+    x = lat.float().view(b, h // 2, w // 2, c // 4, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(b, c // 4, h, w)
+    ch = cond_size // 8
+    x = torch.nn.functional.adaptive_avg_pool2d(x, (ch, ch))
+    x = x.view(b, c // 4, ch // 2, 2, ch // 2, 2).permute(0, 2, 4, 1, 3, 5)
+    return Condition("cot", latents=x.reshape(b, (ch // 2) ** 2, c).to(lat.dtype),
+                     position_delta=[0, -cond_size // 16])
+
+
 def fake_generate(pipe, prompt=None, conditions=None, latents=None, **kw):
     """test-only denoiser: deterministic function of (noise, parent condition, prompt)."""
     cond = conditions[0].latents.float()
@@ -67,7 +82,7 @@ def run_rounds(ctx, tmp):
         dp = RF.sample(noises, "a photo of a cat", upd, refl, rnd, FakePipe(), branch, tmp, CONFIG,
                        dirs["last"], dirs["best"], dirs["bestround"], parents, dirs["mid"], rounds,
                        chains, verifier=StubVerifier("nvila"), reflector=StubReflector(), ctx=ctx,
-                       generate_fn=fake_generate)
+                       generate_fn=fake_generate, condition_fn=fake_condition)
         parents, chains = dp["generated"], dp["chains"]
         upd, refl = dp["refined_prompt"], dp["reflections"]
         log.append({"topk_idx": dp["topk_idx"], "seeds": [c.seed for c in parents],
@@ -139,8 +154,82 @@ def test_world2_gloo_matches_single_process(tmp_path):
     assert r0 == json.loads(json.dumps(single)), "sharded run differs from the single-process run"
 
 
-def test_parent_condition_latents_shape_and_mean():
-    lat = torch.randn(1, 4096, 64).to(torch.bfloat16)
-    c = RF.parent_condition_latents(lat, 1024, 1024, 512)
-    assert c.shape == (1, 1024, 64)
-    assert abs(c.float().mean().item() - lat.float().mean().item()) < 5e-3
+def test_condition_needs_a_vae():
+    """no latent-space stand-in in the product: without a VAE the parent condition raises"""
+    lat = torch.randn(1, 16, 64).to(torch.bfloat16)
+    with pytest.raises(RuntimeError, match="vae"):
+        RF.parent_condition(FakePipe(), Candidate("x.png", 0, latents=lat), H, W, 32, 0)
+
+
+class _FavourRound1(StubVerifier):
+    """scores fall with the round number: the global best is a round-1 candidate"""
+
+    def value(self, cand):
+        rnd = int(os.path.basename(cand.name).split("_round@")[0]) if "_round@" in cand.name else 0
+        return (0.05 / (1 + rnd) if rnd else -0.05) + 1e-4 * (cand.seed % 7)
+
+
+def test_best_of_an_early_round_is_still_written(tmp_path):
+    """the global best of round 1 must reach samples_best/ after round 3."""
+    torch.manual_seed(99)
+    rounds, branch = 3, 4
+    g = torch.Generator().manual_seed(3)
+    parents = [Candidate(f"r0/{i}.png", i, latents=torch.randn(1, 16, 64, generator=g).to(torch.bfloat16))
+               for i in range(branch)]
+    tmp = str(tmp_path)
+    dirs = {k: os.path.join(tmp, k) for k in ("last", "best", "bestround", "mid")}
+    for d in dirs.values():
+        os.makedirs(d)
+    chains = {}
+    upd, refl = ["p"] * branch, [""] * branch
+    ver = _FavourRound1("nvila")
+    for rnd in range(1, rounds + 1):
+        noises = get_noises(S.MAX_SEED, branch, H, W)
+        dp = RF.sample(noises, "p", upd, refl, rnd, FakePipe(), branch, tmp, CONFIG, dirs["last"],
+                       dirs["best"], dirs["bestround"], parents, dirs["mid"], rounds, chains,
+                       verifier=ver, reflector=StubReflector(), ctx=DistCtx(),
+                       generate_fn=fake_generate, condition_fn=fake_condition)
+        parents, chains = dp["generated"], dp["chains"]
+        upd, refl = dp["refined_prompt"], dp["reflections"]
+    best = S.global_best(chains, "nvila")
+    assert os.path.basename(best).startswith("1_round@"), best
+    files = os.listdir(dirs["best"])
+    assert files == ["00000.latent.pt"], files
+    want = torch.load(os.path.join(dirs["mid"], os.path.basename(best)[:-4] + ".latent.pt"))
+    assert torch.equal(torch.load(os.path.join(dirs["best"], files[0])), want)
+    assert len(os.listdir(dirs["bestround"])) == branch
+
+
+class _OpenAIShaped(StubVerifier):
+    def score_one(self, cand, prompt):
+        v = self.value(cand)
+        s = max(0, min(10, int(round(5 + 60.0 * v))))
+        return {"accuracy_to_prompt": {"score": s, "explanation": f"why {cand.seed}"},
+                "overall_score": {"score": s, "explanation": f"overall {cand.seed}"}}
+
+
+def test_openai_shaped_outputs_travel_whole(tmp_path):
+    """every aspect + explanation reaches the reflector and the jsonl."""
+    torch.manual_seed(5)
+    cfg = dict(CONFIG, verifier_args={"name": "openai"})
+    g = torch.Generator().manual_seed(3)
+    parents = [Candidate(f"r0/{i}.png", i, latents=torch.randn(1, 16, 64, generator=g).to(torch.bfloat16))
+               for i in range(3)]
+    tmp = str(tmp_path)
+    dirs = {k: os.path.join(tmp, k) for k in ("last", "best", "bestround", "mid")}
+    for d in dirs.values():
+        os.makedirs(d)
+    seen = {}
+
+    class Refl(StubReflector):
+        def generate_reflections(self, cands, op, cp, refl, evaluations):
+            seen["ev"] = evaluations
+            return super().generate_reflections(cands, op, cp, refl, evaluations)
+    noises = get_noises(S.MAX_SEED, 3, H, W)
+    RF.sample(noises, "p", ["p"] * 3, [""] * 3, 1, FakePipe(), 3, tmp, cfg, dirs["last"], dirs["best"],
+              dirs["bestround"], parents, dirs["mid"], 2, {}, verifier=_OpenAIShaped("openai"),
+              reflector=Refl(), ctx=DistCtx(), generate_fn=fake_generate, condition_fn=fake_condition)
+    ev = [json.loads(e) for e in seen["ev"]]
+    assert all("accuracy_to_prompt" in e and e["overall_score"]["explanation"].startswith("overall") for e in ev)
+    line = json.loads(open(os.path.join(tmp, "best_img_detailedscore.jsonl")).readline())
+    assert "accuracy_to_prompt" in line["evaluation"][0]

@@ -77,7 +77,17 @@ def test_best_per_chain_and_global_best():
 
 def test_unknown_verifier_rejected():
     with pytest.raises(NotImplementedError):
-        S.sort_outputs([], "ours")
+        S.sort_outputs([], "gemini")
+
+
+def test_ours_branch_follows_the_metric_rules():
+    """the Image-Verifier ("ours") returns a scalar reward under choice_of_metric"""
+    outs = [{"Overall": -0.3}, {"Overall": 1.25}, {"Overall": 0.0}]
+    assert [o["Overall"] for o in S.sort_outputs(outs, "ours", "Overall")] == [1.25, 0.0, -0.3]
+    ch = S.update_chains({}, 1, ["a", "b", "c"], outs, [], "ours", "Overall")
+    ch = S.update_chains(ch, 2, ["a1"], [{"Overall": 0.5}], ["a"], "ours", "Overall")
+    assert ch["a"] == {"images": ["a", "a1"], "scores": [-0.3, 0.5]}
+    assert S.best_per_chain(ch, "ours") == ["a1", "b", "c"] and S.global_best(ch, "ours") == "b"
 
 
 def test_records_roundtrip_and_sharding():
