@@ -92,7 +92,8 @@ def test_dit_matches_reference_golden(name):
     assert d.mean() <= 2.0 * e_ref.mean() + 1e-3
 
 
-@pytest.mark.parametrize("name", ["fwdB_small", "fwdB_full", "denoiseB_small"])
+@pytest.mark.parametrize("name", ["fwdB_small", "fwdB_full", "denoiseB_small", "fwdB_deep", "fwdB_mid",
+                                  "fwdB_1024", "denoiseB_28", "denoiseB_1024_28"])
 def test_merged_lora_mode_stays_inside_the_error_budget(name):
     """lora_mode='merged' (peft fuse_lora semantics: condition tokens use bf16(W + BA)) is the fast
     path of the tts loop; it changes three roundings of the low-rank path into one rounding of the
@@ -141,4 +142,83 @@ def test_missing_weights_fail_loudly():
         m(hidden_states=x["latents"], timestep=x["timestep"], guidance=x["guidance"],
           pooled_projections=x["pooled"], encoder_hidden_states=x["prompt_embeds"],
           txt_ids=x["txt_ids"], img_ids=x["img_ids"])
+    m.close()
+
+
+def test_new_adapter_replaces_merged_weights():
+    """ADVICE r01 (medium): in merged mode a second load_lora() (no `mode` argument) must re-merge;
+    the forward has to equal a fresh model loaded with the second adapter, bit for bit."""
+    case = C.CASES["fwdB_small"]
+    model, lora1 = C.build_model(case)
+    lora2 = fo.make_lora_weights(model, case.config(), rank=case.lora_rank, seed=777)
+    x = C.build_inputs(case)
+
+    def fwd(m):
+        out = tranformer_forward(m, x["cond_latents"], x["cond_ids"], None, {}, 0,
+                                 hidden_states=x["latents"], encoder_hidden_states=x["prompt_embeds"],
+                                 pooled_projections=x["pooled"], timestep=x["timestep"],
+                                 img_ids=x["img_ids"], txt_ids=x["txt_ids"], guidance=x["guidance"],
+                                 return_dict=False)[0]
+        torch.cuda.synchronize()
+        return out.cpu()
+    a = B200FluxTransformer2DModel(case.config(), lora_rank=case.lora_rank)
+    a.load_state_dict(model.state_dict())
+    a.load_lora(lora1, mode="merged")
+    o1 = fwd(a)
+    a.load_lora(lora2)            # same mode, new adapter
+    o2 = fwd(a)
+    b = B200FluxTransformer2DModel(case.config(), lora_rank=case.lora_rank)
+    b.load_state_dict(model.state_dict())
+    b.load_lora(lora2, mode="merged")
+    o2_fresh = fwd(b)
+    assert not torch.equal(o1, o2)
+    assert torch.equal(o2, o2_fresh)
+    # reloading base weights after a merge refreshes the merged copies too
+    sd = {k: (v * 0.5 if k.endswith("proj_mlp.weight") else v) for k, v in model.state_dict().items()}
+    a.load_state_dict(sd)
+    b2 = B200FluxTransformer2DModel(case.config(), lora_rank=case.lora_rank)
+    b2.load_state_dict(sd)
+    b2.load_lora(lora2, mode="merged")
+    assert torch.equal(fwd(a), fwd(b2))
+    for m in (a, b, b2):
+        m.close()
+
+
+def test_mismatched_lora_shapes_are_rejected():
+    case = C.CASES["fwdB_small"]
+    m = _build(case)
+    from reflectionflow_b200._lib import RFError
+    D = case.heads * 128
+    with pytest.raises(RFError, match="expects"):
+        m.load_lora({"single_transformer_blocks.0.proj_out": (torch.zeros(8, D), torch.zeros(D, 8))})
+    with pytest.raises(ValueError):
+        m.load_lora({"x_embedder": (torch.zeros(8, 64), torch.zeros(D, 4))})
+    _MODELS.clear()
+
+
+def test_k_only_adapter_is_applied():
+    """a LoRA on to_k alone must not be ignored (q had to be set before)."""
+    case = C.CASES["fwdB_small_nolora"]
+    import dataclasses
+    case_l = dataclasses.replace(case, lora_rank=32)
+    model, _ = C.build_model(case)
+    full = fo.make_lora_weights(model, case.config(), rank=32, seed=5)
+    konly = {k: v for k, v in full.items() if k.endswith("attn.to_k")}
+    assert konly
+    x = C.build_inputs(case)
+    m = B200FluxTransformer2DModel(case.config(), lora_rank=32)
+    m.load_state_dict(model.state_dict())
+    m.load_lora(konly)
+    out = tranformer_forward(m, x["cond_latents"], x["cond_ids"], None, {}, 0, hidden_states=x["latents"],
+                             encoder_hidden_states=x["prompt_embeds"], pooled_projections=x["pooled"],
+                             timestep=x["timestep"], img_ids=x["img_ids"], txt_ids=x["txt_ids"],
+                             guidance=x["guidance"], return_dict=False)[0].cpu().float()
+    ref = fo.transformer_forward(model, x["latents"], x["prompt_embeds"], x["pooled"], x["timestep"],
+                                 x["img_ids"], x["txt_ids"], x["guidance"], x["cond_latents"], x["cond_ids"],
+                                 {}, fo.LoraSet(konly, 1.0)).float()
+    base = fo.transformer_forward(model, x["latents"], x["prompt_embeds"], x["pooled"], x["timestep"],
+                                  x["img_ids"], x["txt_ids"], x["guidance"], x["cond_latents"], x["cond_ids"],
+                                  {}, None).float()
+    assert (ref - base).abs().mean() > 1e-3, "the k-only adapter must matter in the oracle"
+    assert (out - ref).abs().mean() < 0.25 * (ref - base).abs().mean()
     m.close()

@@ -26,7 +26,7 @@ def _models():
     return _CACHE["m"]
 
 
-@pytest.mark.parametrize("height,width", [(64, 1024), (128, 1024), (256, 256), (128, 512)])
+@pytest.mark.parametrize("height,width", [(64, 1024), (128, 1024), (256, 256), (128, 512), (1024, 1024)])
 def test_decode_matches_oracle(height, width):
     ref, ours = _models()
     g = torch.Generator().manual_seed(height * 7 + width)
