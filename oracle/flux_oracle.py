@@ -296,7 +296,7 @@ class CombinedTimestepTextProjEmbeddings(nn.Module):
 def get_1d_rotary_pos_embed(dim: int, pos: torch.Tensor, theta: float = 10000.0):
     """diffusers get_1d_rotary_pos_embed(use_real=True, repeat_interleave_real=True,
     freqs_dtype=float64)."""
-    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2, dtype=torch.float64)[: dim // 2] / dim))
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2, dtype=torch.float64, device=pos.device)[: dim // 2] / dim))
     freqs = torch.outer(pos, freqs)
     cos = freqs.cos().repeat_interleave(2, dim=1).float()
     sin = freqs.sin().repeat_interleave(2, dim=1).float()

@@ -369,7 +369,8 @@ def build_pipeline(config: dict, args, ctx: DistCtx):
     else:
         pipe.text_encoder_hook = HashTextEncoder(cfg.joint_attention_dim, cfg.pooled_projection_dim)
     if lora_path is not None:
-        pipe.transformer.load_lora(synthetic_lora(cfg, seed=1), mode="merged")
+        # "exact" = peft's unfused arithmetic (what the reference runs); "merged" = fuse_lora
+        pipe.transformer.load_lora(synthetic_lora(cfg, seed=1), mode=getattr(args, "lora_mode", None) or "exact")
     pipe.set_progress_bar_config(disable=True)
     return pipe
 

@@ -34,6 +34,8 @@ def parse_cli_args(argv=None):
     parser.add_argument("--text_encoders", choices=("hash", "native"), default="hash",
                         help="--synthetic only: hash embeddings, or random-init T5-XXL + CLIP-L run on the device")
     parser.add_argument("--layers", type=str, default=None, help="debug: 'double,single' layer counts")
+    parser.add_argument("--lora_mode", choices=("exact", "merged"), default="exact",
+                        help="exact = peft's unfused low-rank arithmetic (the reference's); merged = fuse_lora")
     return parser.parse_args(argv)
 
 
