@@ -154,6 +154,8 @@ def test_postprocess_rounding():
 
 def test_against_real_diffusers():
     diffusers = pytest.importorskip("diffusers", reason="diffusers is not installed in this image")
+    if "shims" in (getattr(diffusers, "__file__", "") or "") or not hasattr(diffusers, "AutoencoderKL"):
+        pytest.skip("only the oracle's import shim named `diffusers` is on the path, not the real package")
     ref = diffusers.AutoencoderKL(in_channels=3, out_channels=3, latent_channels=16,
                                   down_block_types=("DownEncoderBlock2D",) * 4,
                                   up_block_types=("UpDecoderBlock2D",) * 4,
