@@ -29,6 +29,8 @@ namespace rf {
 int lora_merge_launch(const bf16* W, const bf16* A, const bf16* B, bf16* Wm, int N, int K, int R,
                       cudaStream_t stream);
 int add2_launch(const bf16* a, const bf16* b, bf16* out, int n, cudaStream_t stream);
+int select_row_launch(const bf16* table, int64_t row_elems, const int* row, bf16* out,
+                      cudaStream_t stream);
 int f32_to_bf16_launch(const float* src, bf16* dst, int n, cudaStream_t stream);
 int gemm_init();
 int attention_init();
@@ -114,6 +116,9 @@ struct rf_dit {
   bf16 *s_tsteps = nullptr, *s_guid = nullptr, *s_zero_one = nullptr;
   float* s_sigmas = nullptr;
   int* s_step = nullptr;
+  // every step's adaLN modulation vectors, computed BEFORE the loop (all timesteps are known up
+  // front): MOD_ALL [n_steps, n_mod]; the captured step only selects its row
+  bf16 *s_mod_all = nullptr, *s_temb_ws = nullptr;
   int s_cap_steps = 0;
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t own_stream = nullptr;  // capture is illegal on the legacy default stream
@@ -403,6 +408,39 @@ int merge_all(rf_dit* h, cudaStream_t s) {
   return 0;
 }
 
+// temb_i = time(t_i) + guidance(g) + text(pooled) for ALL steps, then every adaLN Linear of every
+// block for all steps: the 6.5 GB modulation weight stack is streamed ceil(n/8) times per denoise
+// call instead of once per step.  Same kernels, same per-vector arithmetic as compute_temb + gemv
+// (the GEMV's per-vector summation order does not depend on the batch width): bit-identical.
+int precompute_step_mods(rf_dit* h, int n_steps, const bf16* tsteps, const bf16* guid,
+                         const bf16* pooled, cudaStream_t s) {
+  const int D = h->D;
+  bf16* ws = h->s_temb_ws;  // [n,256] | [n,D] tmp | [n,D] a | [n,D] temb | [256] gp | [D] tmp1 | [D] b | [D] c
+  bf16* tp = ws;
+  bf16* tmp = tp + static_cast<int64_t>(n_steps) * 256;
+  bf16* a = tmp + static_cast<int64_t>(n_steps) * D;
+  bf16* temb = a + static_cast<int64_t>(n_steps) * D;
+  bf16* gp = temb + static_cast<int64_t>(n_steps) * D;
+  bf16 *tmp1 = gp + 256, *b = tmp1 + D, *c = b + D;
+  RF_TRY(rf::timestep_embed_launch(tsteps, nullptr, 1, 1000.0f, tp, n_steps, s));
+  RF_TRY(rf::gemv_launch(tp, 256, n_steps, h->t1.w, h->t1.b, tmp, D, D, 256, 0, s));
+  RF_TRY(rf::gemv_launch(tmp, D, n_steps, h->t2.w, h->t2.b, a, D, D, D, 1, s));
+  RF_TRY(mlp2(h, pooled, h->cfg.pooled_projection_dim, h->p1, h->p2, tmp1, c, s));
+  if (h->cfg.guidance_embeds) {
+    RF_TRY(rf::timestep_embed_launch(guid, nullptr, 1, 1000.0f, gp, 1, s));
+    RF_TRY(mlp2(h, gp, 256, h->g1, h->g2, tmp1, b, s));
+  }
+  for (int i = 0; i < n_steps; ++i) {
+    bf16* ai = a + static_cast<int64_t>(i) * D;
+    bf16* ti = temb + static_cast<int64_t>(i) * D;
+    if (h->cfg.guidance_embeds) RF_TRY(rf::add3_launch(ai, b, c, ti, D, s));
+    else RF_TRY(rf::add2_launch(ai, c, ti, D, s));
+  }
+  RF_TRY(rf::gemv_launch(temb, D, n_steps, h->modW, h->modB, h->s_mod_all, static_cast<int>(h->n_mod),
+                         static_cast<int>(h->n_mod), D, 1, s));
+  return 0;
+}
+
 struct StreamRows {
   int row0, rows;
 };
@@ -410,7 +448,7 @@ struct StreamRows {
 // The body of one DiT forward for one sample.  All pointers are device pointers.
 int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16* pooled,
                     const bf16* tstep, const int* step_idx, const bf16* guid, const bf16* cond_lat,
-                    bf16* out, cudaStream_t s) {
+                    bf16* out, cudaStream_t s, const bf16* mod_all = nullptr) {
   const int D = h->D, D3 = 3 * D, D4 = 4 * D, D5 = 5 * D;
   const bool use_cond = h->n_cond > 0;
   const StreamRows S_txt{0, h->n_txt}, S_img{h->n_txt, h->n_img}, S_cond{h->n_main, h->n_cond};
@@ -441,15 +479,27 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
   RF_TRY(rf::gemm_launch(rf::EPI_BIAS, D, h->cfg.joint_attention_dim, 1, g, s));
 
   // ---- temb and every modulation vector of the step (transformer.py:95-107 + all adaLN linears)
-  RF_TRY(compute_temb(h, tstep, step_idx, guid, pooled, h->temb, s));
-  RF_TRY(rf::gemv_launch(h->temb, D, 1, h->modW, h->modB, h->MOD, static_cast<int>(h->n_mod),
-                         static_cast<int>(h->n_mod), D, 1, s));
+  if (mod_all != nullptr) {  // denoise loop: this step's row of the precomputed table
+    RF_TRY(rf::select_row_launch(mod_all, h->n_mod, step_idx, h->MOD, s));
+  } else {
+    RF_TRY(compute_temb(h, tstep, step_idx, guid, pooled, h->temb, s));
+    RF_TRY(rf::gemv_launch(h->temb, D, 1, h->modW, h->modB, h->MOD, static_cast<int>(h->n_mod),
+                           static_cast<int>(h->n_mod), D, 1, s));
+  }
   const bf16* MOD = h->MOD;
   const bf16* MODC = h->MODC;
 
   auto ln = [&](const StreamRows& sr, const bf16* scale, const bf16* shift) {
     return rf::ln_modulate_launch(rowp(X, D, sr.row0), D, rowp(XN, D, sr.row0), D, sr.rows, D, scale,
                                   shift, sr.rows, 0, s);
+  };
+  // all token streams of a norm in ONE launch: rows are [txt | img | cond] of the joint buffers
+  auto ln3 = [&](const bf16* sc_txt, const bf16* sh_txt, const bf16* sc_img, const bf16* sh_img,
+                 const bf16* sc_cond, const bf16* sh_cond) {
+    const int ends[3] = {h->n_txt, h->n_main, h->N};
+    const bf16* sc[3] = {sc_txt, sc_img, sc_cond};
+    const bf16* sh[3] = {sh_txt, sh_img, sh_cond};
+    return rf::ln_modulate_grouped_launch(X, D, XN, D, D, use_cond ? 3 : 2, ends, sc, sh, s);
   };
   rf::AttnArgs at;
   at.q = QKV; at.k = QKV + D; at.v = QKV + 2 * D; at.ld_qkv = D3;
@@ -464,9 +514,8 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
     const bf16* mt = MOD + mod_double(h, i, 1, 0);
     const bf16* mc = MODC + mod_double(h, i, 0, 0);
     // norm1 / norm1_context
-    RF_TRY(ln(S_img, mi + SCALE_MSA * D, mi + SHIFT_MSA * D));
-    RF_TRY(ln(S_txt, mt + SCALE_MSA * D, mt + SHIFT_MSA * D));
-    if (use_cond) RF_TRY(ln(S_cond, mc + SCALE_MSA * D, mc + SHIFT_MSA * D));
+    RF_TRY(ln3(mt + SCALE_MSA * D, mt + SHIFT_MSA * D, mi + SCALE_MSA * D, mi + SHIFT_MSA * D,
+               mc + SCALE_MSA * D, mc + SHIFT_MSA * D));
     // q|k|v projections + RMSNorm + RoPE, all streams in one grouped launch
     memset(g, 0, sizeof(g));
     g[0].A = rowp(XN, D, S_img.row0); g[0].lda = D; g[0].M = S_img.rows; g[0].W = b.qkv.w;
@@ -519,9 +568,8 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
     }
     RF_TRY(rf::gemm_launch(rf::EPI_GATE_RES, D, D, ng, g, s));
     // norm2 + modulate
-    RF_TRY(ln(S_img, mi + SCALE_MLP * D, mi + SHIFT_MLP * D));
-    RF_TRY(ln(S_txt, mt + SCALE_MLP * D, mt + SHIFT_MLP * D));
-    if (use_cond) RF_TRY(ln(S_cond, mc + SCALE_MLP * D, mc + SHIFT_MLP * D));
+    RF_TRY(ln3(mt + SCALE_MLP * D, mt + SHIFT_MLP * D, mi + SCALE_MLP * D, mi + SHIFT_MLP * D,
+               mc + SCALE_MLP * D, mc + SHIFT_MLP * D));
     // MLP in (GELU-tanh) -> ACT[:, D:5D]
     memset(g, 0, sizeof(g));
     g[0].A = rowp(XN, D, S_img.row0); g[0].lda = D; g[0].M = S_img.rows; g[0].W = b.ff1.w;
@@ -567,8 +615,8 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
     const SingleBlk& b = h->sgl[i];
     const bf16* mm = MOD + mod_single(h, i, 0);
     const bf16* mc = MODC + mod_single(h, i, 0);
-    RF_TRY(ln(S_main, mm + 1 * D, mm + 0 * D));
-    if (use_cond) RF_TRY(ln(S_cond, mc + 1 * D, mc + 0 * D));
+    // txt and img rows share the block's vectors; the cond rows use the cond_temb ones
+    RF_TRY(ln3(mm + 1 * D, mm + 0 * D, mm + 1 * D, mm + 0 * D, mc + 1 * D, mc + 0 * D));
     // q|k|v
     memset(g, 0, sizeof(g));
     g[0].A = XN; g[0].lda = D; g[0].M = S_main.rows; g[0].W = b.qkv.w; g[0].bias = b.qkv.b;
@@ -665,6 +713,25 @@ __global__ void add2_kernel(const bf16* a, const bf16* b, bf16* out, int n) {
 }
 int add2_launch(const bf16* a, const bf16* b, bf16* out, int n, cudaStream_t stream) {
   add2_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a, b, out, n);
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+// out[0:row_elems] = table[*row]  (16-byte vectors; row_elems % 8 == 0)
+__global__ void select_row_kernel(const uint4* __restrict__ table, int64_t row_vecs,
+                                  const int* __restrict__ row, uint4* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < row_vecs) out[i] = table[static_cast<int64_t>(*row) * row_vecs + i];
+}
+int select_row_launch(const bf16* table, int64_t row_elems, const int* row, bf16* out,
+                      cudaStream_t stream) {
+  if (row_elems % 8 != 0) {
+    set_error("select_row: row length must be a multiple of 8");
+    return -1;
+  }
+  const int64_t vecs = row_elems / 8;
+  select_row_kernel<<<static_cast<unsigned>((vecs + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(table), vecs, row, reinterpret_cast<uint4*>(out));
   RF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -1036,6 +1103,10 @@ int rf_dit_denoise(rf_dit* h, void* latents_inout, const void* txt, const void* 
     h->s_tsteps = static_cast<bf16*>(p);
     if (dev_alloc(h, &p, static_cast<size_t>(n_steps + 1) * 4, true)) return -2;
     h->s_sigmas = static_cast<float*>(p);
+    if (dev_alloc(h, &p, static_cast<size_t>(n_steps) * h->n_mod * 2, true)) return -2;
+    h->s_mod_all = static_cast<bf16*>(p);
+    if (dev_alloc(h, &p, (static_cast<size_t>(n_steps) * (256 + 3 * h->D) + 256 + 3 * h->D) * 2, true)) return -2;
+    h->s_temb_ws = static_cast<bf16*>(p);
     h->s_cap_steps = n_steps;
     drop_graph(h);  // graph referenced the old arrays
   }
@@ -1065,6 +1136,7 @@ int rf_dit_denoise(rf_dit* h, void* latents_inout, const void* txt, const void* 
           static_cast<size_t>(h->n_cond) * C * 2, cudaMemcpyDeviceToDevice, s));
       RF_TRY(compute_cond_mod(h, h->s_pooled, s));  // hoisted out of the step loop
     }
+    RF_TRY(precompute_step_mods(h, n_steps, h->s_tsteps, h->s_guid, h->s_pooled, s));
     RF_CHECK_CUDA(cudaMemsetAsync(h->s_step, 0, sizeof(int), s));
     if (!h->graph_exec) {
       // capture one step: forward -> Euler update -> step counter
@@ -1073,7 +1145,8 @@ int rf_dit_denoise(rf_dit* h, void* latents_inout, const void* txt, const void* 
       RF_CHECK_CUDA(cudaStreamSynchronize(s));
       RF_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       int erc = enqueue_forward(h, h->s_lat, h->s_txt, h->s_pooled, h->s_tsteps, h->s_step,
-                                h->s_guid, h->n_cond > 0 ? h->s_cond : nullptr, h->s_v, s);
+                                h->s_guid, h->n_cond > 0 ? h->s_cond : nullptr, h->s_v, s,
+                                h->s_mod_all);
       if (!erc) erc = rf::euler_step_launch(h->s_lat, h->s_v, h->s_sigmas, h->s_step, h->n_img * C, s);
       if (!erc) erc = rf::advance_step_launch(h->s_step, s);
       cudaError_t ce = cudaStreamEndCapture(s, &graph);

@@ -11,6 +11,8 @@
 //   timestep_embed: sinusoidal projection (diffusers Timesteps(256, flip_sin_to_cos=True))
 //   euler_step    : FlowMatchEulerDiscreteScheduler.step (generate.py:276)
 // All of them keep the reference's bf16 rounding points.
+#include <cstring>
+
 #include "rf_internal.h"
 #include "rf_ptx.cuh"
 
@@ -26,19 +28,27 @@ __device__ __forceinline__ float warp_sum(float v) {
 // one warp per row; dim <= 3072 and dim % 256 == 0 (each lane owns dim/256 16-byte chunks)
 static constexpr int kLnMaxChunks = 12;
 
+struct LnGroups {  // up to 3 row ranges (token streams) of one joint buffer, each with its own adaLN vectors
+  int row_end[3];
+  const bf16* scale[3];
+  const bf16* shift[3];
+  int ngroups;
+};
+
 __global__ void __launch_bounds__(256, 3)
 ln_modulate_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int ldo, int rows,
-                   int dim, const bf16* __restrict__ scale, const bf16* __restrict__ shift,
-                   int rows_per_batch, int mod_stride) {
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                   int dim, const __grid_constant__ LnGroups G, int rows_per_batch, int mod_stride) {
   const int lane = threadIdx.x & 31;
-  if (warp_global >= rows) return;
-  const int row = warp_global;
-  const int b = row / rows_per_batch;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int nch = dim >> 8;  // 16-byte chunks per lane
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps_total) {
+  const int b = row / rows_per_batch;
+  int gi = 0;
+  if (G.ngroups > 1 && row >= G.row_end[0]) gi = 1;
+  if (G.ngroups > 2 && row >= G.row_end[1]) gi = 2;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx);
-  const uint4* sc = reinterpret_cast<const uint4*>(scale + static_cast<size_t>(b) * mod_stride);
-  const uint4* sh = reinterpret_cast<const uint4*>(shift + static_cast<size_t>(b) * mod_stride);
+  const uint4* sc = reinterpret_cast<const uint4*>(G.scale[gi] + static_cast<size_t>(b) * mod_stride);
+  const uint4* sh = reinterpret_cast<const uint4*>(G.shift[gi] + static_cast<size_t>(b) * mod_stride);
   // the row stays in registers as packed bf16 (48 regs) so that 32 warps/SM are resident
   uint4 raw[kLnMaxChunks];
 #pragma unroll
@@ -106,25 +116,64 @@ ln_modulate_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, 
       orow[lane + 32 * i] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
     }
   }
+  }  // row loop
 }
 
-int ln_modulate_launch(const bf16* x, int ldx, bf16* out, int ldo, int rows, int dim,
-                       const bf16* scale, const bf16* shift, int rows_per_batch, int mod_stride,
-                       cudaStream_t stream) {
+static int ln_launch_common(const bf16* x, int ldx, bf16* out, int ldo, int rows, int dim, const LnGroups& G,
+                            int rows_per_batch, int mod_stride, cudaStream_t stream) {
   if (dim % 256 != 0 || dim > 256 * kLnMaxChunks || dim <= 0) {
     set_error("ln_modulate: dim must be a multiple of 256, <= 3072");
     return -1;
   }
   if (rows <= 0) return 0;
-  const int warps_per_block = 8;
-  const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  // one warp per row, rows dealt round-robin to a grid that is at most one resident wave
+  // (3 blocks x 8 warps per SM): no block-granular tail
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  int blocks = (rows + 7) / 8;
+  if (blocks > sms * 3) blocks = sms * 3;
   ProfScope prof("ln_modulate", 0.0, 4.0 * rows * dim, stream);
-  ln_modulate_kernel<<<blocks, 256, 0, stream>>>(x, ldx, out, ldo, rows, dim, scale, shift,
-                                                 rows_per_batch > 0 ? rows_per_batch : rows,
-                                                 mod_stride);
+  ln_modulate_kernel<<<blocks, 256, 0, stream>>>(x, ldx, out, ldo, rows, dim, G,
+                                                 rows_per_batch > 0 ? rows_per_batch : rows, mod_stride);
   RF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+// grouped form: rows [0, row_end[0]) use (scale[0], shift[0]), [row_end[0], row_end[1]) the next ...
+int ln_modulate_grouped_launch(const bf16* x, int ldx, bf16* out, int ldo, int dim, int ngroups,
+                               const int* row_end, const bf16* const* scale, const bf16* const* shift,
+                               cudaStream_t stream) {
+  if (ngroups < 1 || ngroups > 3) {
+    set_error("ln_modulate: 1..3 row groups");
+    return -1;
+  }
+  LnGroups G;
+  memset(&G, 0, sizeof(G));
+  G.ngroups = ngroups;
+  for (int i = 0; i < ngroups; ++i) {
+    G.row_end[i] = row_end[i];
+    G.scale[i] = scale[i];
+    G.shift[i] = shift[i];
+  }
+  return ln_launch_common(x, ldx, out, ldo, row_end[ngroups - 1], dim, G, 0, 0, stream);
+}
+
+int ln_modulate_launch(const bf16* x, int ldx, bf16* out, int ldo, int rows, int dim,
+                       const bf16* scale, const bf16* shift, int rows_per_batch, int mod_stride,
+                       cudaStream_t stream) {
+  LnGroups G;
+  memset(&G, 0, sizeof(G));
+  G.ngroups = 1;
+  G.row_end[0] = rows;
+  G.scale[0] = scale;
+  G.shift[0] = shift;
+  return ln_launch_common(x, ldx, out, ldo, rows, dim, G, rows_per_batch, mod_stride, stream);
 }
 
 // ------------------------------------------------------------------------- gemv

@@ -93,6 +93,11 @@ int attention_launch(const AttnArgs& a, cudaStream_t stream);
 int ln_modulate_launch(const bf16* x, int ldx, bf16* out, int ldo, int rows, int dim,
                        const bf16* scale, const bf16* shift, int rows_per_batch, int mod_stride,
                        cudaStream_t stream);
+// same, for up to 3 consecutive row ranges of one buffer (token streams), each with its own vectors:
+// rows [0, row_end[0]) use (scale[0], shift[0]), rows [row_end[0], row_end[1]) the next, ...
+int ln_modulate_grouped_launch(const bf16* x, int ldx, bf16* out, int ldo, int dim, int ngroups,
+                               const int* row_end, const bf16* const* scale, const bf16* const* shift,
+                               cudaStream_t stream);
 // y[n] = bf16(sum_k act(x[k]) * W[n, k] + b[n]) for `batch` input vectors.
 //   act: 0 identity, 1 = bf16(silu(x))
 int gemv_launch(const bf16* x, int ldx, int batch, const bf16* W, const bf16* bias, bf16* y,

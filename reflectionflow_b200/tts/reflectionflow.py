@@ -41,8 +41,8 @@ RETRY_DELAY = 2
 _SAVER = None
 _PENDING: Dict[str, "object"] = {}
 # every candidate of the current prompt's tree by name (the reference re-opens PNGs from disk when it
-# copies a best image of an EARLIER round, tts_reflectionflow.py:408-446; we keep the packed latents,
-# 0.5 MB each, and re-decode on demand)
+# copies a best image of an EARLIER round, tts_reflectionflow.py:408-446; a tree is 32 candidates of
+# 0.5 MB latents + 3 MB pixels, so they simply stay referenced until the next prompt)
 _REGISTRY: Dict[str, Dict[str, Candidate]] = {}
 
 
@@ -51,12 +51,6 @@ def _registry(root_dir: str, search_round: int) -> Dict[str, Candidate]:
         _REGISTRY.clear()  # one prompt's tree at a time
     return _REGISTRY.setdefault(root_dir, {})
 
-
-def _slim(cand: Candidate):
-    """Drop the pixel copies of a candidate that left the active window (latents stay)."""
-    cand.image_u8 = None
-    cand.image = None
-    cand.__dict__.pop("_png", None)
 
 
 def _submit_save(path: str, job: Callable[[], None]):
@@ -253,7 +247,6 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
     S.update_chains(chains, search_round, full_imgnames, outputs, selected_imgs, verifier_name,
                     choice_of_metric)
     by_name = _registry(root_dir, search_round)
-    active = {c.name for c in list(imagetoupdate) + new_cands}
     for c in list(imagetoupdate) + new_cands:
         by_name[c.name] = c
 
@@ -277,9 +270,6 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
             best = S.global_best(chains, verifier_name)
             # the reference names this file with a leaked loop index (App. B.9); we use 00000
             _save_candidate(materialise(best), os.path.join(sample_path_best, f"{0:05}.png"))
-    for name, c in by_name.items():  # older rounds keep latents only
-        if name not in active:
-            _slim(c)
 
     datapoint = {"original_prompt": original_prompt, "search_round": search_round,
                  "num_noises": len(noises), "choice_of_metric": choice_of_metric,
