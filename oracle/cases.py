@@ -87,6 +87,9 @@ CASES = {c.name: c for c in [
     Case("denoiseB_1024_28", double=1, single=2, n_txt=512, height=1024, width=1024, cond_size=512,
          lora_rank=32, steps=28, seed=21),
     Case("denoiseB_deep_28", double=19, single=38, steps=28, cond_size=128, lora_rank=32, seed=22),
+    # full width with >= 128 condition tokens: the fused-LoRA condition GEMMs (gemm2_lora_launch)
+    Case("fwdB_full_c256", heads=24, double=1, single=1, joint_dim=4096, pooled_dim=768, n_txt=512,
+         cond_size=256, lora_rank=32, seed=23),
 ]}
 
 

@@ -33,6 +33,7 @@ int select_row_launch(const bf16* table, int64_t row_elems, const int* row, bf16
                       cudaStream_t stream);
 int f32_to_bf16_launch(const float* src, bf16* dst, int n, cudaStream_t stream);
 int gemm_init();
+int lora_down_init();
 int attention_init();
 int gemv_init();
 }
@@ -65,6 +66,7 @@ struct DoubleBlk {
   bf16 *norm_q, *norm_k, *norm_added_q, *norm_added_k;
   LoraT l_norm1, l_q, l_k, l_v, l_out, l_ff2;
   bf16* qkvA = nullptr;  // [192, D] = stacked A of to_q/to_k/to_v
+  bf16* qkvB = nullptr;  // [3D, 64] = stacked B (rows of the packed q|k|v projection)
   bf16 *qkv_m = nullptr, *to_out_m = nullptr, *ff2_m = nullptr;  // merged W + B A (fuse_lora mode)
 };
 struct SingleBlk {
@@ -72,6 +74,7 @@ struct SingleBlk {
   bf16 *norm_q, *norm_k;
   LoraT l_norm, l_q, l_k, l_v, l_mlp, l_out;
   bf16* qkvA = nullptr;
+  bf16* qkvB = nullptr;
   bf16 *qkv_m = nullptr, *mlp_m = nullptr, *out_m = nullptr;
 };
 
@@ -109,6 +112,7 @@ struct rf_dit {
   // ---- workspace
   bf16 *X = nullptr, *XN = nullptr, *QKV = nullptr, *ACT = nullptr, *MOD = nullptr, *MODC = nullptr;
   bf16 *LT = nullptr, *LL = nullptr;  // LoRA temporaries: T [rows, 192], L [rows, 4D]
+  void* lora_ws = nullptr;            // split-K workspace of the LoRA down-projection
   bf16 *emb_tmp = nullptr;            // small vectors for the temb path
   bf16 *temb = nullptr, *ctemb = nullptr;
   // ---- staging for the graph-captured denoise loop
@@ -163,12 +167,12 @@ Lin new_lin(rf_dit* h, Arena& ar, const std::string& mod, int out, int in) {
 }
 
 void new_lora(rf_dit* h, Arena& ar, const std::string& mod, LoraT& t, int out, int in,
-              bf16* A_view = nullptr) {
+              bf16* A_view = nullptr, bf16* B_view = nullptr) {
   if (h->cfg.lora_rank <= 0) return;
   t.in = in;
   t.out = out;
   t.A = A_view ? A_view : ar.take(static_cast<int64_t>(kLoraPad) * in);
-  t.B = ar.take(static_cast<int64_t>(out) * kLoraPad);
+  t.B = B_view ? B_view : ar.take(static_cast<int64_t>(out) * kLoraPad);
   // unset targets must contribute exactly zero (a q-only adapter still runs the stacked q|k|v path)
   if (t.A) cudaMemset(t.A, 0, static_cast<size_t>(kLoraPad) * in * 2);
   if (t.B) cudaMemset(t.B, 0, static_cast<size_t>(out) * kLoraPad * 2);
@@ -209,14 +213,18 @@ int build_storage(rf_dit* h) {
     b.add_qkv = new_lin(h, ar, "", 3 * D, D);
     const char* nm[3] = {"to_q", "to_k", "to_v"};
     const char* an[3] = {"add_q_proj", "add_k_proj", "add_v_proj"};
-    if (c.lora_rank > 0) b.qkvA = ar.take(static_cast<int64_t>(3 * kLoraPad) * D);
+    if (c.lora_rank > 0) {
+      b.qkvA = ar.take(static_cast<int64_t>(3 * kLoraPad) * D);
+      b.qkvB = ar.take(static_cast<int64_t>(3 * D) * kLoraPad);
+    }
     LoraT* lq[3] = {&b.l_q, &b.l_k, &b.l_v};
     for (int j = 0; j < 3; ++j) {
       reg_lin(h, p + "attn." + nm[j], b.qkv.w + static_cast<int64_t>(j) * D * D, b.qkv.b + j * D, D, D);
       reg_lin(h, p + "attn." + an[j], b.add_qkv.w + static_cast<int64_t>(j) * D * D,
               b.add_qkv.b + j * D, D, D);
       new_lora(h, ar, p + "attn." + nm[j], *lq[j], D, D,
-               b.qkvA ? b.qkvA + static_cast<int64_t>(j) * kLoraPad * D : nullptr);
+               b.qkvA ? b.qkvA + static_cast<int64_t>(j) * kLoraPad * D : nullptr,
+               b.qkvB ? b.qkvB + static_cast<int64_t>(j) * D * kLoraPad : nullptr);
     }
     b.norm_q = ar.take(128); reg(h, p + "attn.norm_q.weight", b.norm_q, 128);
     b.norm_k = ar.take(128); reg(h, p + "attn.norm_k.weight", b.norm_k, 128);
@@ -240,13 +248,17 @@ int build_storage(rf_dit* h) {
     reg_lin(h, p + "norm.linear", h->modW + mo * D, h->modB + mo, 3 * D, D);
     new_lora(h, ar, p + "norm.linear", b.l_norm, 3 * D, D);
     b.qkv = new_lin(h, ar, "", 3 * D, D);
-    if (c.lora_rank > 0) b.qkvA = ar.take(static_cast<int64_t>(3 * kLoraPad) * D);
+    if (c.lora_rank > 0) {
+      b.qkvA = ar.take(static_cast<int64_t>(3 * kLoraPad) * D);
+      b.qkvB = ar.take(static_cast<int64_t>(3 * D) * kLoraPad);
+    }
     const char* nm[3] = {"to_q", "to_k", "to_v"};
     LoraT* lq[3] = {&b.l_q, &b.l_k, &b.l_v};
     for (int j = 0; j < 3; ++j) {
       reg_lin(h, p + "attn." + nm[j], b.qkv.w + static_cast<int64_t>(j) * D * D, b.qkv.b + j * D, D, D);
       new_lora(h, ar, p + "attn." + nm[j], *lq[j], D, D,
-               b.qkvA ? b.qkvA + static_cast<int64_t>(j) * kLoraPad * D : nullptr);
+               b.qkvA ? b.qkvA + static_cast<int64_t>(j) * kLoraPad * D : nullptr,
+               b.qkvB ? b.qkvB + static_cast<int64_t>(j) * D * kLoraPad : nullptr);
     }
     b.norm_q = ar.take(128); reg(h, p + "attn.norm_q.weight", b.norm_q, 128);
     b.norm_k = ar.take(128); reg(h, p + "attn.norm_k.weight", b.norm_k, 128);
@@ -493,6 +505,21 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
     return rf::ln_modulate_launch(rowp(X, D, sr.row0), D, rowp(XN, D, sr.row0), D, sr.rows, D, scale,
                                   shift, sr.rows, 0, s);
   };
+  // A grouped GEMM whose LAST group is the condition stream carrying a LoRA (exact mode).  Fast path:
+  // T = bf16(x A^T) (one skinny GEMM), the other streams as one grouped launch, then the condition
+  // stream with the low-rank k-block fused (gemm2_lora_launch) — L = T B^T never reaches HBM.  Small /
+  // odd shapes keep the unfused path: L materialised by two GEMMs and added in the epilogue (`addend`).
+  auto gemm_cond_lora = [&](int epi, int N, int K, int ngr, rf::GemmGroupArgs* gr, const bf16* loraA,
+                            int t_cols, const bf16* loraB, int sec_cols, auto&& unfused_term) -> int {
+    rf::GemmGroupArgs& gc = gr[ngr - 1];
+    if (rf::gemm2_lora_eligible(epi, N, K, gc)) {
+      RF_TRY(rf::lora_down_launch(gc.A, gc.lda, gc.M, K, loraA, t_cols, h->LT, t_cols, h->lora_ws, s));
+      if (ngr > 1) RF_TRY(rf::gemm_launch(epi, N, K, ngr - 1, gr, s));
+      return rf::gemm2_lora_launch(epi, N, K, gc, h->LT, t_cols, loraB, sec_cols, s);
+    }
+    RF_TRY(unfused_term(gc));
+    return rf::gemm_launch(epi, N, K, ngr, gr, s);
+  };
   // all token streams of a norm in ONE launch: rows are [txt | img | cond] of the joint buffers
   auto ln3 = [&](const bf16* sc_txt, const bf16* sh_txt, const bf16* sc_img, const bf16* sh_img,
                  const bf16* sc_cond, const bf16* sh_cond) {
@@ -528,6 +555,7 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
     g[1].rope_cos = h->rope_cos; g[1].rope_sin = h->rope_sin;
     g[1].norm_q = b.norm_added_q; g[1].norm_k = b.norm_added_k;
     ng = 2;
+    bool cond_lora = false;
     if (use_cond) {
       g[2] = g[0];
       g[2].A = rowp(XN, D, S_cond.row0); g[2].M = S_cond.rows;
@@ -536,12 +564,19 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       if (h->use_merged) {
         g[2].W = b.qkv_m;
       } else if (b.l_q.set || b.l_k.set || b.l_v.set) {
-        RF_TRY(lora_term_qkv(h, b.qkvA, b.l_q, b.l_k, b.l_v, g[2].A, D, S_cond.rows, h->LL, D3, s));
-        g[2].addend = h->LL; g[2].ldadd = D3;
+        cond_lora = true;
       }
       ng = 3;
     }
-    RF_TRY(rf::gemm_launch(rf::EPI_QKV, D3, D, ng, g, s));
+    if (cond_lora) {
+      RF_TRY(gemm_cond_lora(rf::EPI_QKV, D3, D, ng, g, b.qkvA, 3 * kLoraPad, b.qkvB, D, [&](rf::GemmGroupArgs& gc) {
+        RF_TRY(lora_term_qkv(h, b.qkvA, b.l_q, b.l_k, b.l_v, gc.A, D, S_cond.rows, h->LL, D3, s));
+        gc.addend = h->LL; gc.ldadd = D3;
+        return 0;
+      }));
+    } else {
+      RF_TRY(rf::gemm_launch(rf::EPI_QKV, D3, D, ng, g, s));
+    }
     // joint attention -> ACT[:, 0:D]
     at.out = ACT; at.ldo = D5;
     RF_TRY(rf::attention_launch(at, s));
@@ -554,6 +589,7 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
     g[1].bias = b.to_add_out.b; g[1].out = rowp(X, D, 0); g[1].ldo = D;
     g[1].res = g[1].out; g[1].ldr = D; g[1].gate = mt + GATE_MSA * D;
     ng = 2;
+    cond_lora = false;
     if (use_cond) {
       g[2] = g[0];
       g[2].A = rowp(ACT, D5, S_cond.row0); g[2].M = S_cond.rows;
@@ -561,12 +597,19 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       if (h->use_merged) {
         g[2].W = b.to_out_m;
       } else if (b.l_out.set) {
-        RF_TRY(lora_term(h, b.l_out, g[2].A, D5, S_cond.rows, h->LL, D, s));
-        g[2].addend = h->LL; g[2].ldadd = D;
+        cond_lora = true;
       }
       ng = 3;
     }
-    RF_TRY(rf::gemm_launch(rf::EPI_GATE_RES, D, D, ng, g, s));
+    if (cond_lora) {
+      RF_TRY(gemm_cond_lora(rf::EPI_GATE_RES, D, D, ng, g, b.l_out.A, kLoraPad, b.l_out.B, 0, [&](rf::GemmGroupArgs& gc) {
+        RF_TRY(lora_term(h, b.l_out, gc.A, D5, S_cond.rows, h->LL, D, s));
+        gc.addend = h->LL; gc.ldadd = D;
+        return 0;
+      }));
+    } else {
+      RF_TRY(rf::gemm_launch(rf::EPI_GATE_RES, D, D, ng, g, s));
+    }
     // norm2 + modulate
     RF_TRY(ln3(mt + SCALE_MLP * D, mt + SHIFT_MLP * D, mi + SCALE_MLP * D, mi + SHIFT_MLP * D,
                mc + SCALE_MLP * D, mc + SHIFT_MLP * D));
@@ -594,6 +637,7 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
     g[1].A = rowp(ACT, D5, 0) + D; g[1].M = S_txt.rows; g[1].W = b.ffc2.w; g[1].bias = b.ffc2.b;
     g[1].out = rowp(X, D, 0); g[1].res = g[1].out; g[1].gate = mt + GATE_MLP * D;
     ng = 2;
+    cond_lora = false;
     if (use_cond) {
       g[2] = g[0];
       g[2].A = rowp(ACT, D5, S_cond.row0) + D; g[2].M = S_cond.rows;
@@ -601,12 +645,19 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       if (h->use_merged) {
         g[2].W = b.ff2_m;
       } else if (b.l_ff2.set) {
-        RF_TRY(lora_term(h, b.l_ff2, g[2].A, D5, S_cond.rows, h->LL, D, s));
-        g[2].addend = h->LL; g[2].ldadd = D;
+        cond_lora = true;
       }
       ng = 3;
     }
-    RF_TRY(rf::gemm_launch(rf::EPI_GATE_RES, D, D4, ng, g, s));
+    if (cond_lora) {
+      RF_TRY(gemm_cond_lora(rf::EPI_GATE_RES, D, D4, ng, g, b.l_ff2.A, kLoraPad, b.l_ff2.B, 0, [&](rf::GemmGroupArgs& gc) {
+        RF_TRY(lora_term(h, b.l_ff2, gc.A, D5, S_cond.rows, h->LL, D, s));
+        gc.addend = h->LL; gc.ldadd = D;
+        return 0;
+      }));
+    } else {
+      RF_TRY(rf::gemm_launch(rf::EPI_GATE_RES, D, D4, ng, g, s));
+    }
   }
 
   // ================= single-stream blocks (block.py:275-333) =================
@@ -623,6 +674,7 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
     g[0].out = QKV; g[0].ldo = D3; g[0].rope_cos = h->rope_cos; g[0].rope_sin = h->rope_sin;
     g[0].norm_q = b.norm_q; g[0].norm_k = b.norm_k;
     ng = 1;
+    bool cond_lora = false;
     if (use_cond) {
       g[1] = g[0];
       g[1].A = rowp(XN, D, S_cond.row0); g[1].M = S_cond.rows;
@@ -631,17 +683,25 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       if (h->use_merged) {
         g[1].W = b.qkv_m;
       } else if (b.l_q.set || b.l_k.set || b.l_v.set) {
-        RF_TRY(lora_term_qkv(h, b.qkvA, b.l_q, b.l_k, b.l_v, g[1].A, D, S_cond.rows, h->LL, D3, s));
-        g[1].addend = h->LL; g[1].ldadd = D3;
+        cond_lora = true;
       }
       ng = 2;
     }
-    RF_TRY(rf::gemm_launch(rf::EPI_QKV, D3, D, ng, g, s));
+    if (cond_lora) {
+      RF_TRY(gemm_cond_lora(rf::EPI_QKV, D3, D, ng, g, b.qkvA, 3 * kLoraPad, b.qkvB, D, [&](rf::GemmGroupArgs& gc) {
+        RF_TRY(lora_term_qkv(h, b.qkvA, b.l_q, b.l_k, b.l_v, gc.A, D, S_cond.rows, h->LL, D3, s));
+        gc.addend = h->LL; gc.ldadd = D3;
+        return 0;
+      }));
+    } else {
+      RF_TRY(rf::gemm_launch(rf::EPI_QKV, D3, D, ng, g, s));
+    }
     // proj_mlp + GELU -> ACT[:, D:5D]
     memset(g, 0, sizeof(g));
     g[0].A = XN; g[0].lda = D; g[0].M = S_main.rows; g[0].W = b.mlp.w; g[0].bias = b.mlp.b;
     g[0].out = ACT + D; g[0].ldo = D5;
     ng = 1;
+    cond_lora = false;
     if (use_cond) {
       g[1] = g[0];
       g[1].A = rowp(XN, D, S_cond.row0); g[1].M = S_cond.rows;
@@ -649,12 +709,19 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       if (h->use_merged) {
         g[1].W = b.mlp_m;
       } else if (b.l_mlp.set) {
-        RF_TRY(lora_term(h, b.l_mlp, g[1].A, D, S_cond.rows, h->LL, D4, s));
-        g[1].addend = h->LL; g[1].ldadd = D4;
+        cond_lora = true;
       }
       ng = 2;
     }
-    RF_TRY(rf::gemm_launch(rf::EPI_GELU, D4, D, ng, g, s));
+    if (cond_lora) {
+      RF_TRY(gemm_cond_lora(rf::EPI_GELU, D4, D, ng, g, b.l_mlp.A, kLoraPad, b.l_mlp.B, 0, [&](rf::GemmGroupArgs& gc) {
+        RF_TRY(lora_term(h, b.l_mlp, gc.A, D, S_cond.rows, h->LL, D4, s));
+        gc.addend = h->LL; gc.ldadd = D4;
+        return 0;
+      }));
+    } else {
+      RF_TRY(rf::gemm_launch(rf::EPI_GELU, D4, D, ng, g, s));
+    }
     // attention -> ACT[:, 0:D]
     at.out = ACT; at.ldo = D5;
     RF_TRY(rf::attention_launch(at, s));
@@ -663,6 +730,7 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
     g[0].A = ACT; g[0].lda = D5; g[0].M = S_main.rows; g[0].W = b.out.w; g[0].bias = b.out.b;
     g[0].out = X; g[0].ldo = D; g[0].res = X; g[0].ldr = D; g[0].gate = mm + 2 * D;
     ng = 1;
+    cond_lora = false;
     if (use_cond) {
       g[1] = g[0];
       g[1].A = rowp(ACT, D5, S_cond.row0); g[1].M = S_cond.rows;
@@ -670,12 +738,19 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       if (h->use_merged) {
         g[1].W = b.out_m;
       } else if (b.l_out.set) {
-        RF_TRY(lora_term(h, b.l_out, g[1].A, D5, S_cond.rows, h->LL, D, s));
-        g[1].addend = h->LL; g[1].ldadd = D;
+        cond_lora = true;
       }
       ng = 2;
     }
-    RF_TRY(rf::gemm_launch(rf::EPI_GATE_RES, D, D5, ng, g, s));
+    if (cond_lora) {
+      RF_TRY(gemm_cond_lora(rf::EPI_GATE_RES, D, D5, ng, g, b.l_out.A, kLoraPad, b.l_out.B, 0, [&](rf::GemmGroupArgs& gc) {
+        RF_TRY(lora_term(h, b.l_out, gc.A, D5, S_cond.rows, h->LL, D, s));
+        gc.addend = h->LL; gc.ldadd = D;
+        return 0;
+      }));
+    } else {
+      RF_TRY(rf::gemm_launch(rf::EPI_GATE_RES, D, D5, ng, g, s));
+    }
   }
 
   // ================= norm_out + proj_out (transformer.py:241-244) =================
@@ -813,7 +888,7 @@ int rf_dit_create(const rf_dit_config* cfg, rf_dit** out) {
   }
   cudaGetDevice(&h->device);
   // opt in to the large dynamic shared-memory carve-outs up front (not inside a graph capture)
-  if (rf::gemm_init() || rf::attention_init() || rf::gemv_init()) {
+  if (rf::gemm_init() || rf::lora_down_init() || rf::attention_init() || rf::gemv_init()) {
     delete h;
     return -2;
   }
@@ -981,6 +1056,12 @@ int rf_dit_prepare(rf_dit* h, int batch, int n_txt, int n_img, int n_cond, const
     const size_t lrows = static_cast<size_t>(std::max(n_cond, 1));
     if (!(p = A(std::max(lrows * 3 * kLoraPad * 2, static_cast<size_t>(8 * D) * 2)))) return -2; h->LT = static_cast<bf16*>(p);
     if (!(p = A(std::max(lrows * 4 * D * 2, static_cast<size_t>(8 * D) * 2)))) return -2; h->LL = static_cast<bf16*>(p);
+    {
+      const size_t wsb = rf::lora_down_workspace_bytes(std::max(n_cond, 1), 3 * kLoraPad);
+      if (!(p = A(wsb))) return -2;
+      h->lora_ws = p;
+      RF_CHECK_CUDA(cudaMemsetAsync(p, 0, wsb, s));
+    }
     if (!(p = A(static_cast<size_t>(512 + 4 * D) * 2))) return -2; h->emb_tmp = static_cast<bf16*>(p);
     if (!(p = A(static_cast<size_t>(D) * 2))) return -2; h->temb = static_cast<bf16*>(p);
     if (!(p = A(static_cast<size_t>(D) * 2))) return -2; h->ctemb = static_cast<bf16*>(p);

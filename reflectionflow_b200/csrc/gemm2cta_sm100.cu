@@ -40,6 +40,10 @@ struct Cfg2 {
 
 struct alignas(64) Gemm2Group {
   CUtensorMap tmA, tmB, tmOut, tmRes;
+  // fused peft LoRA (kLora kernels): T = bf16(x A^T) [M, 64 per section] and the B factor [N, 64];
+  // a tile in column section s = n0 / lora_sec_cols reads T columns [64 s, 64 s + 64)
+  CUtensorMap tmT, tmLB;
+  int lora_sec_cols;
   const bf16* bias;
   const bf16* addend;
   const bf16* gate;
@@ -155,9 +159,14 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&acc)[64]) {
   tmem_ld_wait();
 }
 
-template <int EPI, int kBN>
+// kLora (kBN == 128 only): the tile also accumulates L = T B^T (ONE extra 64-deep k-block, its own TMEM
+// accumulator: columns [2 kBN, 4 kBN)) and the epilogue forms bf16(bf16(acc + bias) + bf16(L)) — peft's
+// unfused LoRA arithmetic (lora_controller.py:5-42) without materialising L in HBM.
+template <int EPI, int kBN, bool kLora = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_kernel(const __grid_constant__ Gemm2Params p) {
+  static_assert(!kLora || kBN == 128, "the LoRA accumulator needs the 128-wide tile (TMEM: 4 x 128 columns)");
+  constexpr int kTmemCols = kLora ? 4 * kBN : 2 * kBN;
   constexpr int kStages = Cfg2<kBN>::kStages;
   constexpr int kStage = Cfg2<kBN>::kStage;
   extern __shared__ uint8_t smem_raw[];
@@ -184,6 +193,10 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       tma_prefetch_desc(&p.g[g].tmA);
       tma_prefetch_desc(&p.g[g].tmB);
       tma_prefetch_desc(&p.g[g].tmOut);
+      if constexpr (kLora) {
+        tma_prefetch_desc(&p.g[g].tmT);
+        tma_prefetch_desc(&p.g[g].tmLB);
+      }
     }
   }
   if (warp == 1 && lane == 0) {
@@ -199,7 +212,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc_2cta<2 * kBN>(tmem_slot);
+    tmem_alloc_2cta<kTmemCols>(tmem_slot);
     tmem_relinquish_2cta();
   }
   tc_fence_before();
@@ -218,6 +231,15 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       const int my_n = tc.n0 + rank * (kBN / 2);
       PixTile pt{0, 0};
       if (G.conv_w != 0) pt = pix_tile(G, my_m);
+      if constexpr (kLora) {  // the low-rank k-block first: T rows of this CTA, B rows of its half tile
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStage;
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStage);
+        const int tcol = G.lora_sec_cols > 0 ? (tc.n0 / G.lora_sec_cols) * 64 : 0;
+        tma_load_2d_2cta(sa, &G.tmT, &full_bar[stage], tcol, my_m);
+        tma_load_2d_2cta(sa + kStageA, &G.tmLB, &full_bar[stage], 0, my_n);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * kStage;
@@ -261,6 +283,18 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kBN;
       long long stall = 0;
+      if constexpr (kLora) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kStage);
+        const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(sa + kStageA, 16, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          mma_ss_2cta(d_tmem + 2 * kBN, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
+        tc_commit_2cta(&empty_bar[stage], 3);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
       for (int kb = 0; kb < p.num_kb; ++kb) {
         if (tr) {
           const long long c0 = clock64();
@@ -318,6 +352,21 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       if (etr && eti < 16) p.trace[eti * 8 + 4] = clock64();
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_off + as * kBN;
+      // v = bf16(v + bf16(L)): the low-rank term of this 64-column chunk from its own accumulator
+      auto lora_add = [&](uint32_t col, float (&v)[64]) {
+        if constexpr (kLora) {
+          uint32_t accl[64];
+          tmem_ld64(taddr + 2 * kBN + col, accl);
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            float l0 = __uint_as_float(accl[i]), l1 = __uint_as_float(accl[i + 1]);
+            bf16_round2(l0, l1);
+            v[i] += l0;
+            v[i + 1] += l1;
+            bf16_round2(v[i], v[i + 1]);
+          }
+        }
+      };
 
       // issue the box store of chunk `cc` (all 128 epilogue threads call this)
       auto publish = [&](const float (&v)[64], int col) {
@@ -339,12 +388,12 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       };
 
       if constexpr (EPI == EPI_QKV) {
-        static_assert(EPI != EPI_QKV || kBN == 256, "QKV epilogue needs two heads per tile");
+        static_assert(kBN % 128 == 0, "QKV epilogue: a head is 128 columns");
         const int inner = p.N / 3;
         const float* cosr = G.rope_cos + static_cast<size_t>(row_c) * 64;
         const float* sinr = G.rope_sin + static_cast<size_t>(row_c) * 64;
 #pragma unroll 1
-        for (int hc = 0; hc < 2; ++hc) {
+        for (int hc = 0; hc < kBN / 128; ++hc) {
           const int col_h = tc.n0 + hc * 128;
           const int section = col_h / inner;  // 0 q, 1 k, 2 v
           const bf16* bias_h = G.bias ? G.bias + col_h : nullptr;
@@ -358,6 +407,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
               tmem_ld64(taddr + hc * 128 + c * 64, acc);
               float v[64];
               linear_round64(acc, bias_h ? bias_h + c * 64 : nullptr, add_h ? add_h + c * 64 : nullptr, v);
+              lora_add(hc * 128 + c * 64, v);
 #pragma unroll
               for (int i = 0; i < 64; ++i) ss = __fmaf_rn(v[i], v[i], ss);
             }
@@ -381,6 +431,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
             tmem_ld64(taddr + hc * 128 + c * 64, acc);
             float v[64];
             linear_round64(acc, bias_h ? bias_h + c * 64 : nullptr, add_h ? add_h + c * 64 : nullptr, v);
+            lora_add(hc * 128 + c * 64, v);
             if (section != 2) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
@@ -441,6 +492,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
           float v[64];
           linear_round64(acc, G.bias ? G.bias + tc.n0 + c * 64 : nullptr,
                          add_r ? add_r + c * 64 : nullptr, v);
+          lora_add(c * 64, v);
           if constexpr (EPI == EPI_GELU) {
 #pragma unroll
             for (int i = 0; i < 64; i += 2) {
@@ -481,16 +533,16 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
   cluster_sync_all();  // no CTA may exit (or free TMEM) while its pair can still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc_2cta<2 * kBN>(tmem_base);
+    tmem_dealloc_2cta<kTmemCols>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------ host
-template <int EPI, int BN>
+template <int EPI, int BN, bool LORA = false>
 static int set_attr2() {
   static bool done = false;
   if (!done) {
-    RF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI, BN>,
+    RF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI, BN, LORA>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmem));
     done = true;
   }
@@ -498,13 +550,15 @@ static int set_attr2() {
 }
 int gemm2_init() {
   return (set_attr2<EPI_BIAS, 256>() | set_attr2<EPI_GELU, 256>() | set_attr2<EPI_GATE_RES, 256>() |
-          set_attr2<EPI_QKV, 256>() | set_attr2<EPI_BIAS, 128>() | set_attr2<EPI_GATE_RES, 128>())
+          set_attr2<EPI_QKV, 256>() | set_attr2<EPI_BIAS, 128>() | set_attr2<EPI_GATE_RES, 128>() |
+          set_attr2<EPI_GELU, 128, true>() | set_attr2<EPI_GATE_RES, 128, true>() |
+          set_attr2<EPI_QKV, 128, true>())
              ? -2
              : 0;
 }
 
 long long* dbg_get_gemm_trace();
-template <int EPI, int BN>
+template <int EPI, int BN, bool LORA = false>
 static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t stream) {
   Gemm2Params p = p_in;
   p.trace = dbg_get_gemm_trace();
@@ -514,14 +568,14 @@ static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t
     p.dbg_skip = skip;
   }
 #endif
-  if (int rc = set_attr2<EPI, BN>()) return rc;
+  if (int rc = set_attr2<EPI, BN, LORA>()) return rc;
   static const char* kNames[4] = {"gemm_bias", "gemm_gelu", "gemm_gate_res", "gemm_qkv_rms_rope"};
   const char* name = p.g[0].conv_w ? (EPI == EPI_GATE_RES ? "conv_res" : "conv_bias") : kNames[EPI];
   ProfScope prof(name, 2.0 * rows * p.N * p.K,
                  2.0 * (rows * p.K / (p.g[0].conv_w ? p.g[0].conv_taps : 1) +
                         static_cast<double>(p.ngroups) * p.N * p.K + rows * p.N),
                  stream);
-  gemm2_kernel<EPI, BN><<<2 * pairs, kThreads2, Cfg2<BN>::kSmem, stream>>>(p);
+  gemm2_kernel<EPI, BN, LORA><<<2 * pairs, kThreads2, Cfg2<BN>::kSmem, stream>>>(p);
   RF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -618,6 +672,75 @@ int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups
     rows += a.M;
   }
   return gemm2_dispatch(epi, p, tiles, rows, stream);
+}
+
+// One token stream (the condition tokens) with peft LoRA fused: out = epi(bf16(bf16(A W^T + b) + bf16(T B^T))),
+// T = bf16(A lora_A^T) computed beforehand ([M, ldT]; columns [64 s, 64 s + 64) belong to output section
+// s = n / sec_cols when sec_cols > 0 — the stacked q|k|v projection), lora_B [N, 64] (rank zero-padded to 64).
+bool gemm2_lora_eligible(int epi, int N, int K, const GemmGroupArgs& a) {
+  if (epi != EPI_GELU && epi != EPI_GATE_RES && epi != EPI_QKV) return false;
+  if (N % 128 != 0 || K % kBK != 0 || a.M < 128 || a.addend != nullptr) return false;
+  if (epi == EPI_QKV && N % 384 != 0) return false;
+  if ((a.ldo * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(a.out) & 15)) return false;
+  if (epi == EPI_GATE_RES && ((a.ldr * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(a.res) & 15))) return false;
+  return true;
+}
+int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16* T, int ldT,
+                      const bf16* loraB, int sec_cols, cudaStream_t stream) {
+  Gemm2Params p;
+  memset(&p, 0, sizeof(p));
+  p.ngroups = 1;
+  p.N = N;
+  p.K = K;
+  p.bn = 128;
+  p.n_tiles = N / p.bn;
+  p.num_kb = K / kBK;
+  p.band = p.n_tiles <= 24 ? p.n_tiles : 8;  // same W-slice footprint per band as the 256-wide raster
+  Gemm2Group& d = p.g[0];
+  int rc = make_tmap_2d(&d.tmA, a.A, a.M, K, a.lda, kRows);
+  if (rc) return rc;
+  rc = make_tmap_2d(&d.tmB, a.W, N, K, K, p.bn / 2);
+  if (rc) return rc;
+  rc = make_tmap_2d(&d.tmOut, a.out, a.M, N, a.ldo, kRows);
+  if (rc) return rc;
+  const int t_cols = sec_cols > 0 ? (N / sec_cols) * 64 : 64;
+  rc = make_tmap_2d(&d.tmT, T, a.M, t_cols, ldT, kRows);
+  if (rc) return rc;
+  rc = make_tmap_2d(&d.tmLB, loraB, N, 64, 64, p.bn / 2);
+  if (rc) return rc;
+  if (epi == EPI_GATE_RES) {
+    if (a.res == nullptr || a.gate == nullptr) {
+      set_error("gemm2_lora_launch: EPI_GATE_RES needs res and gate");
+      return -1;
+    }
+    rc = make_tmap_2d(&d.tmRes, a.res, a.M, N, a.ldr, kRows);
+    if (rc) return rc;
+  }
+  if (epi == EPI_QKV && (!a.rope_cos || !a.rope_sin || !a.norm_q || !a.norm_k)) {
+    set_error("gemm2_lora_launch: EPI_QKV needs rope tables and norm weights");
+    return -1;
+  }
+  d.bias = a.bias; d.addend = nullptr; d.gate = a.gate;
+  d.rope_cos = a.rope_cos; d.rope_sin = a.rope_sin; d.norm_q = a.norm_q; d.norm_k = a.norm_k;
+  d.M = a.M; d.ldadd = 0;
+  d.lora_sec_cols = sec_cols;
+  d.m_pairs = (a.M + 2 * kRows - 1) / (2 * kRows);
+  d.tile_begin = 0;
+  const int tiles = d.m_pairs * p.n_tiles;
+  p.total_tiles = tiles;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int pairs = sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  switch (epi) {
+    case EPI_GELU: return launch2<EPI_GELU, 128, true>(p, pairs, a.M, stream);
+    case EPI_GATE_RES: return launch2<EPI_GATE_RES, 128, true>(p, pairs, a.M, stream);
+    case EPI_QKV: return launch2<EPI_QKV, 128, true>(p, pairs, a.M, stream);
+    default: break;
+  }
+  set_error("gemm2_lora_launch: unsupported epilogue");
+  return -1;
 }
 
 // 3x3 (taps = 9) or 1x1 (taps = 1) convolution, stride 1 (zero padding 1) or stride 2 (diffusers

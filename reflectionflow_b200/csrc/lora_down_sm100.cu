@@ -1,0 +1,240 @@
+// lora_down_sm100.cu — the LoRA down-projection of the condition tokens as a split-K skinny GEMM.
+//
+//   T[M, NT] = bf16( X[M, K] @ A[NT, K]^T ),   NT = 64 (one target) | 192 (stacked q|k|v) | 256
+//
+// peft computes lora_A(x) as its own bf16 Linear (lora_controller.py:5-42 toggles the scaling of
+// unfused LoraLayers), so T is rounded to bf16 before the up-projection; the up-projection itself is
+// fused into the condition stream's main GEMM (gemm2cta_sm100.cu, kLora).  The product is tiny
+// (M = 1024 condition tokens, NT <= 256) but K runs up to 15360: one CTA per 128-row tile would chain
+// 240 k-blocks on 8 SMs.  Here every (m tile, K split) pair is a CTA — tcgen05.mma 128 x NT x 16 from a
+// TMA ring, fp32 partial to a workspace — and the LAST CTA of an m tile to finish sums the partials in
+// split order (deterministic) and writes the bf16 rows.  One launch, no atomics on the data.
+#include <cuda.h>
+
+#include "rf_internal.h"
+#include "rf_ptx.cuh"
+
+namespace rf {
+
+static constexpr int kLdThreads = 256;
+static constexpr int kLdStages = 4;
+static constexpr int kLdMaxSplits = 16;
+
+struct alignas(64) LoraDownParams {
+  CUtensorMap tmX, tmA;
+  float* ws;            // [splits][m_tiles * 128][NT] fp32 partials
+  unsigned* counters;   // [m_tiles], zero between launches (the last CTA re-arms its counter)
+  bf16* T;
+  int ldT, M, num_kb, splits, kb_per, m_tiles;
+};
+
+template <int NT>
+struct LdCfg {
+  static constexpr int kStageA = 128 * 64 * 2;
+  static constexpr int kStageB = NT * 64 * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kTmemCols = NT <= 64 ? 64 : 256;
+  static constexpr int kSmem = kLdStages * kStage + 1024 + 256;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kLdThreads, 1) lora_down_kernel(const __grid_constant__ LoraDownParams p) {
+  constexpr int kStage = LdCfg<NT>::kStage;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kLdStages * kStage);
+  uint64_t* empty_bar = full_bar + kLdStages;
+  uint64_t* tfull_bar = empty_bar + kLdStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  uint32_t* last_flag = tmem_slot + 1;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mt = blockIdx.x / p.splits;
+  const int sp = blockIdx.x - mt * p.splits;
+  const int kb0 = sp * p.kb_per;
+  const int kb1 = min(p.num_kb, kb0 + p.kb_per);
+  const int nkb = kb1 - kb0;  // >= 1 by construction of the launch
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmA);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kLdStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<LdCfg<NT>::kTmemCols>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* sa = smem + stage * kStage;
+      mbar_arrive_expect_tx(&full_bar[stage], kStage);
+      tma_load_2d(sa, &p.tmX, &full_bar[stage], kb * 64, mt * 128);
+      tma_load_2d(sa + LdCfg<NT>::kStageA, &p.tmA, &full_bar[stage], kb * 64, 0);
+      if (++stage == kLdStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + stage * kStage);
+      const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
+      const uint64_t bdesc = make_smem_desc(sa + LdCfg<NT>::kStageA, 16, 1024, 2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+      tc_commit(&empty_bar[stage]);
+      if (++stage == kLdStages) { stage = 0; phase ^= 1; }
+    }
+    tc_commit(tfull_bar);
+  } else if (warp >= 4) {
+    const int ew = warp & 3;
+    const int r_in = ew * 32 + lane;
+    const int row = mt * 128 + r_in;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    const size_t rows_pad = static_cast<size_t>(p.m_tiles) * 128;
+    float* wrow = p.ws + (static_cast<size_t>(sp) * rows_pad + row) * NT;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < NT / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      tmem_ld_wait();
+      float4* dst = reinterpret_cast<float4*>(wrow + c * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        dst[q] = make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]),
+                             __uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]));
+    }
+    // ---- last CTA of this m tile reduces the splits in order (threadfence reduction pattern)
+    __threadfence();
+    named_bar_sync(2, 128);
+    if (warp == 4 && lane == 0) {
+      const unsigned prev = atomicAdd(&p.counters[mt], 1u);
+      *last_flag = (prev == static_cast<unsigned>(p.splits - 1)) ? 1u : 0u;
+    }
+    named_bar_sync(2, 128);
+    if (*last_flag != 0u) {
+      __threadfence();
+      if (row < p.M) {
+        bf16* trow = p.T + static_cast<size_t>(row) * p.ldT;
+#pragma unroll 1
+        for (int c = 0; c < NT / 8; ++c) {
+          float a[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = 0.f;
+          for (int s = 0; s < p.splits; ++s) {
+            const float4* src = reinterpret_cast<const float4*>(p.ws + (static_cast<size_t>(s) * rows_pad + row) * NT + c * 8);
+            const float4 u = __ldcg(src), v = __ldcg(src + 1);
+            a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+            a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(a[0], a[1]);
+          o.y = pack_bf16x2(a[2], a[3]);
+          o.z = pack_bf16x2(a[4], a[5]);
+          o.w = pack_bf16x2(a[6], a[7]);
+          *reinterpret_cast<uint4*>(trow + c * 8) = o;
+        }
+      }
+      named_bar_sync(2, 128);
+      if (warp == 4 && lane == 0) p.counters[mt] = 0u;  // re-arm for the next launch on this stream
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<LdCfg<NT>::kTmemCols>(tmem_base);
+  }
+}
+
+template <int NT>
+static int ld_set_attr() {
+  static bool done = false;
+  if (!done) {
+    RF_CHECK_CUDA(cudaFuncSetAttribute(lora_down_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       LdCfg<NT>::kSmem));
+    done = true;
+  }
+  return 0;
+}
+int lora_down_init() { return (ld_set_attr<64>() | ld_set_attr<192>() | ld_set_attr<256>()) ? -2 : 0; }
+
+size_t lora_down_workspace_bytes(int M, int NT) {
+  const size_t m_tiles = (static_cast<size_t>(M) + 127) / 128;
+  return kLdMaxSplits * m_tiles * 128 * NT * sizeof(float) + m_tiles * sizeof(unsigned) + 256;
+}
+
+// ws: lora_down_workspace_bytes(M, NT) bytes, ZERO-INITIALISED once by the caller (the counters live at
+// its end and are re-armed by the kernel).
+int lora_down_launch(const bf16* X, int ldx, int M, int K, const bf16* A, int NT, bf16* T, int ldT,
+                     void* ws, cudaStream_t stream) {
+  if ((NT != 64 && NT != 192 && NT != 256) || K % 64 != 0 || K <= 0 || M <= 0 || (ldT * 2) % 16 != 0) {
+    set_error("lora_down: NT must be 64, 192 or 256, K a multiple of 64");
+    return -1;
+  }
+  LoraDownParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = make_tmap_2d(&p.tmX, X, M, K, ldx, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&p.tmA, A, NT, K, K, NT);
+  if (rc) return rc;
+  p.m_tiles = (M + 127) / 128;
+  p.num_kb = K / 64;
+  // >= 6 k-blocks per CTA, at most kLdMaxSplits splits, and no more CTAs than fit one wave
+  int splits = p.num_kb / 6;
+  if (splits < 1) splits = 1;
+  if (splits > kLdMaxSplits) splits = kLdMaxSplits;
+  while (splits > 1 && splits * p.m_tiles > 148) --splits;
+  p.kb_per = (p.num_kb + splits - 1) / splits;
+  p.splits = (p.num_kb + p.kb_per - 1) / p.kb_per;  // every split non-empty
+  const size_t rows_pad = static_cast<size_t>(p.m_tiles) * 128;
+  p.ws = static_cast<float*>(ws);
+  p.counters = reinterpret_cast<unsigned*>(static_cast<uint8_t*>(ws) +
+                                           kLdMaxSplits * rows_pad * NT * sizeof(float));
+  p.T = T;
+  p.ldT = ldT;
+  p.M = M;
+  const int grid = p.m_tiles * p.splits;
+  ProfScope prof("lora_down", 2.0 * M * NT * static_cast<double>(K), 2.0 * (static_cast<double>(M) * K + static_cast<double>(NT) * K), stream);
+  switch (NT) {
+    case 64:
+      if ((rc = ld_set_attr<64>())) return rc;
+      lora_down_kernel<64><<<grid, kLdThreads, LdCfg<64>::kSmem, stream>>>(p);
+      break;
+    case 192:
+      if ((rc = ld_set_attr<192>())) return rc;
+      lora_down_kernel<192><<<grid, kLdThreads, LdCfg<192>::kSmem, stream>>>(p);
+      break;
+    default:
+      if ((rc = ld_set_attr<256>())) return rc;
+      lora_down_kernel<256><<<grid, kLdThreads, LdCfg<256>::kSmem, stream>>>(p);
+      break;
+  }
+  RF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace rf

@@ -73,6 +73,21 @@ struct GemmGroupArgs {
 int gemm_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups,
                 cudaStream_t stream);
 
+// One token stream with peft's unfused LoRA arithmetic fused into the GEMM (gemm2cta_sm100.cu):
+//   out = epi( bf16( bf16(A W^T + b) + bf16(T loraB^T) ) ),  T = bf16(A loraA^T) computed beforehand.
+// T: [M, ldT]; with sec_cols > 0 output section s = n / sec_cols reads T columns [64 s, 64 s + 64)
+// (stacked q|k|v); loraB: [N, 64] (rank zero-padded to 64).
+bool gemm2_lora_eligible(int epi, int N, int K, const GemmGroupArgs& a);
+int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16* T, int ldT,
+                      const bf16* loraB, int sec_cols, cudaStream_t stream);
+
+// LoRA down-projection of one token stream: T[M, NT] = bf16(X[M, K] @ A[NT, K]^T), NT = 64 | 192 | 256,
+// split-K over the SMs with a deterministic in-kernel reduction (lora_down_sm100.cu).  `ws` holds
+// lora_down_workspace_bytes(M, NT) bytes and must be zeroed once before its first use.
+size_t lora_down_workspace_bytes(int M, int NT);
+int lora_down_launch(const bf16* X, int ldx, int M, int K, const bf16* A, int NT, bf16* T, int ldT,
+                     void* ws, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------- attention
 // Non-causal softmax(Q K^T / sqrt(128)) V over one joint token sequence.
 // qkv: [n_tok, ld_qkv] with q at column 0, k at +q_stride... (see attn_sm100.cu)

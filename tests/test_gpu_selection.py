@@ -29,13 +29,15 @@ def _rank(latents, seeds, verifier_name):
     return topk_idx, outs, vals
 
 
-@pytest.mark.parametrize("case_name,mode", [("denoiseA_28", None), ("denoiseB_28", "exact"),
-                                            ("denoiseB_28", "merged")])
-def test_selection_indices_match_the_oracle_loop(case_name, mode):
+# seeds of the global RNG chosen (on the CPU oracle) so that the eight candidates' scores are not
+# accidentally within bf16 noise of each other: min gap 1.3e-3 (A, seed 21) / 1.0e-3 (B, seed 9)
+@pytest.mark.parametrize("case_name,mode,rng_seed", [("denoiseA_28", None, 21), ("denoiseB_28", "exact", 9),
+                                                     ("denoiseB_28", "merged", 9)])
+def test_selection_indices_match_the_oracle_loop(case_name, mode, rng_seed):
     case = C.CASES[case_name]
     model, lora = C.build_model(case)
     x = C.build_inputs(case)
-    torch.manual_seed(2024)
+    torch.manual_seed(rng_seed)
     noises = get_noises(S.MAX_SEED, N_CAND, case.height, case.width)
     seeds = list(noises)
     m = B200FluxTransformer2DModel(case.config(), lora_rank=case.lora_rank or 0)
