@@ -120,6 +120,8 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 8) {
     // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====
@@ -468,8 +470,7 @@ int attention_launch(const AttnArgs& a, cudaStream_t stream) {
   const double n = a.n_tok;
   ProfScope prof("attention", 4.0 * n * n * 128.0 * a.heads * a.batch,
                  2.0 * 4.0 * n * 128.0 * a.heads * a.batch, stream);
-  attn_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(p);
-  RF_CHECK_CUDA(cudaGetLastError());
+  RF_CHECK_CUDA(launch_pdl(attn_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmem, stream, p));
   count_launch();
   return 0;
 }

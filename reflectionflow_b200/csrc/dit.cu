@@ -795,6 +795,8 @@ int add2_launch(const bf16* a, const bf16* b, bf16* out, int n, cudaStream_t str
 // out[0:row_elems] = table[*row]  (16-byte vectors; row_elems % 8 == 0)
 __global__ void select_row_kernel(const uint4* __restrict__ table, int64_t row_vecs,
                                   const int* __restrict__ row, uint4* __restrict__ out) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: see rf_ptx.cuh
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < row_vecs) out[i] = table[static_cast<int64_t>(*row) * row_vecs + i];
 }
@@ -805,9 +807,8 @@ int select_row_launch(const bf16* table, int64_t row_elems, const int* row, bf16
     return -1;
   }
   const int64_t vecs = row_elems / 8;
-  select_row_kernel<<<static_cast<unsigned>((vecs + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const uint4*>(table), vecs, row, reinterpret_cast<uint4*>(out));
-  RF_CHECK_CUDA(cudaGetLastError());
+  RF_CHECK_CUDA(launch_pdl(select_row_kernel, dim3(static_cast<unsigned>((vecs + 255) / 256)), dim3(256), 0, stream,
+                           reinterpret_cast<const uint4*>(table), vecs, row, reinterpret_cast<uint4*>(out)));
   count_launch();
   return 0;
 }

@@ -38,6 +38,8 @@ struct LnGroups {  // up to 3 row ranges (token streams) of one joint buffer, ea
 __global__ void __launch_bounds__(256, 3)
 ln_modulate_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int ldo, int rows,
                    int dim, const __grid_constant__ LnGroups G, int rows_per_batch, int mod_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int nch = dim >> 8;  // 16-byte chunks per lane
@@ -138,9 +140,8 @@ static int ln_launch_common(const bf16* x, int ldx, bf16* out, int ldo, int rows
   int blocks = (rows + 7) / 8;
   if (blocks > sms * 3) blocks = sms * 3;
   ProfScope prof("ln_modulate", 0.0, 4.0 * rows * dim, stream);
-  ln_modulate_kernel<<<blocks, 256, 0, stream>>>(x, ldx, out, ldo, rows, dim, G,
-                                                 rows_per_batch > 0 ? rows_per_batch : rows, mod_stride);
-  RF_CHECK_CUDA(cudaGetLastError());
+  RF_CHECK_CUDA(launch_pdl(ln_modulate_kernel, dim3(blocks), dim3(256), 0, stream, x, ldx, out, ldo, rows, dim, G,
+                           rows_per_batch > 0 ? rows_per_batch : rows, mod_stride));
   count_launch();
   return 0;
 }
@@ -183,6 +184,8 @@ __global__ void __launch_bounds__(256)
 gemv_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ W,
             const bf16* __restrict__ bias, bf16* __restrict__ y, int ldy, int N, int K, int act) {
   extern __shared__ float xs[];  // [NB][K]
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
     const int b = i / K, k = i - b * K;
     float v = __bfloat162float(x[static_cast<size_t>(b) * ldx + k]);
@@ -254,8 +257,7 @@ static int gemv_launch_nb(const bf16* x, int ldx, const bf16* W, const bf16* bia
   int blocks = (N + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope prof("gemv", 2.0 * NB * N * K, 2.0 * N * K, stream);
-  gemv_kernel<NB><<<blocks, 256, smem, stream>>>(x, ldx, W, bias, y, ldy, N, K, act);
-  RF_CHECK_CUDA(cudaGetLastError());
+  RF_CHECK_CUDA(launch_pdl(gemv_kernel<NB>, dim3(blocks), dim3(256), smem, stream, x, ldx, W, bias, y, ldy, N, K, act));
   count_launch();
   return 0;
 }
@@ -329,6 +331,8 @@ int add3_launch(const bf16* a, const bf16* b, const bf16* c, bf16* out, int n,
 __global__ void euler_step_kernel(bf16* __restrict__ x, const bf16* __restrict__ v,
                                   const float* __restrict__ sigmas, const int* __restrict__ step,
                                   int n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   const int s = *step;
@@ -350,16 +354,18 @@ int euler_step_launch(bf16* x, const bf16* v, const float* sigmas, const int* st
     return -1;
   }
   const int threads = n / 8;
-  euler_step_kernel<<<(threads + 255) / 256, 256, 0, stream>>>(x, v, sigmas, step, n);
-  RF_CHECK_CUDA(cudaGetLastError());
+  RF_CHECK_CUDA(launch_pdl(euler_step_kernel, dim3((threads + 255) / 256), dim3(256), 0, stream, x, v, sigmas, step, n));
   count_launch();
   return 0;
 }
 
-__global__ void advance_step_kernel(int* step) { *step += 1; }
+__global__ void advance_step_kernel(int* step) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *step += 1;
+}
 int advance_step_launch(int* step, cudaStream_t stream) {
-  advance_step_kernel<<<1, 1, 0, stream>>>(step);
-  RF_CHECK_CUDA(cudaGetLastError());
+  RF_CHECK_CUDA(launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, stream, step));
   count_launch();
   return 0;
 }

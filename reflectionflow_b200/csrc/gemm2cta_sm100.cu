@@ -219,6 +219,8 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
   cluster_sync_all();  // barrier inits + TMEM allocation of BOTH CTAs visible before any remote op
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; operands are ready from here on
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -399,9 +401,13 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
           const bf16* bias_h = G.bias ? G.bias + col_h : nullptr;
           const bf16* add_h = G.addend ? G.addend + static_cast<size_t>(row_c) * G.ldadd + col_h : nullptr;
           float rinv = 0.f;
+          // ONE pass over TMEM per head: the bf16-rounded linear output of the 128 columns stays in
+          // registers as packed bf16 pairs (exact: the values are already bf16) between the
+          // sum-of-squares pass and the normalise / RoPE pass
+          uint32_t keep[2][32];
           if (section != 2) {
             float ss = 0.f;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < 2; ++c) {
               uint32_t acc[64];
               tmem_ld64(taddr + hc * 128 + c * 64, acc);
@@ -409,51 +415,46 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
               linear_round64(acc, bias_h ? bias_h + c * 64 : nullptr, add_h ? add_h + c * 64 : nullptr, v);
               lora_add(hc * 128 + c * 64, v);
 #pragma unroll
-              for (int i = 0; i < 64; ++i) ss = __fmaf_rn(v[i], v[i], ss);
+              for (int i = 0; i < 64; i += 2) {
+                ss = __fmaf_rn(v[i], v[i], ss);
+                ss = __fmaf_rn(v[i + 1], v[i + 1], ss);
+                keep[c][i >> 1] = pack_bf16x2(v[i], v[i + 1]);
+              }
             }
             const float var = __fdiv_rn(ss, 128.0f);
             rinv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-6f)));
           }
           const bf16* nw = (section == 0) ? G.norm_q : G.norm_k;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            float cs[32], sn[32];
-            if (section != 2) {  // this row's 32 (cos, sin) pairs of the chunk; issued before the math
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(cosr + c * 32) + q);
-                const float4 b = __ldg(reinterpret_cast<const float4*>(sinr + c * 32) + q);
-                cs[q * 4] = a.x; cs[q * 4 + 1] = a.y; cs[q * 4 + 2] = a.z; cs[q * 4 + 3] = a.w;
-                sn[q * 4] = b.x; sn[q * 4 + 1] = b.y; sn[q * 4 + 2] = b.z; sn[q * 4 + 3] = b.w;
-              }
-            }
-            uint32_t acc[64];
-            tmem_ld64(taddr + hc * 128 + c * 64, acc);
+          for (int c = 0; c < 2; ++c) {
             float v[64];
-            linear_round64(acc, bias_h ? bias_h + c * 64 : nullptr, add_h ? add_h + c * 64 : nullptr, v);
-            lora_add(hc * 128 + c * 64, v);
             if (section != 2) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 float w[8];
                 ld8(nw + c * 64 + q * 8, w);
+                // this row's 4 (cos, sin) pairs of the 8 columns
+                const float4 cq = __ldg(reinterpret_cast<const float4*>(cosr + c * 32) + q);
+                const float4 sq = __ldg(reinterpret_cast<const float4*>(sinr + c * 32) + q);
+                const float cs[4] = {cq.x, cq.y, cq.z, cq.w}, sn[4] = {sq.x, sq.y, sq.z, sq.w};
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) {
-                  float y0 = __fmul_rn(v[q * 8 + i], rinv), y1 = __fmul_rn(v[q * 8 + i + 1], rinv);
+                  const float2 x = unpack_bf16x2(keep[c][(q * 8 + i) >> 1]);
+                  float y0 = __fmul_rn(x.x, rinv), y1 = __fmul_rn(x.y, rinv);
                   bf16_round2(y0, y1);  // RMSNorm -> bf16
                   y0 = __fmul_rn(y0, w[i]);
                   y1 = __fmul_rn(y1, w[i + 1]);
                   bf16_round2(y0, y1);  // * weight -> bf16
-                  v[q * 8 + i] = y0;
-                  v[q * 8 + i + 1] = y1;
+                  // interleaved-pair RoPE, fp32, one rounding at the pack
+                  v[q * 8 + i] = __fadd_rn(__fmul_rn(y0, cs[i >> 1]), __fmul_rn(-y1, sn[i >> 1]));
+                  v[q * 8 + i + 1] = __fadd_rn(__fmul_rn(y1, cs[i >> 1]), __fmul_rn(y0, sn[i >> 1]));
                 }
               }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {  // interleaved-pair RoPE, fp32, one rounding at the pack
-                const float x0 = v[2 * j], x1 = v[2 * j + 1];
-                v[2 * j] = __fadd_rn(__fmul_rn(x0, cs[j]), __fmul_rn(-x1, sn[j]));
-                v[2 * j + 1] = __fadd_rn(__fmul_rn(x1, cs[j]), __fmul_rn(x0, sn[j]));
-              }
+            } else {
+              uint32_t acc[64];
+              tmem_ld64(taddr + hc * 128 + c * 64, acc);
+              linear_round64(acc, bias_h ? bias_h + c * 64 : nullptr, add_h ? add_h + c * 64 : nullptr, v);
+              lora_add(hc * 128 + c * 64, v);
             }
             publish(v, col_h + c * 64);
             ++cc;
@@ -575,8 +576,7 @@ static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t
                  2.0 * (rows * p.K / (p.g[0].conv_w ? p.g[0].conv_taps : 1) +
                         static_cast<double>(p.ngroups) * p.N * p.K + rows * p.N),
                  stream);
-  gemm2_kernel<EPI, BN, LORA><<<2 * pairs, kThreads2, Cfg2<BN>::kSmem, stream>>>(p);
-  RF_CHECK_CUDA(cudaGetLastError());
+  RF_CHECK_CUDA(launch_pdl(gemm2_kernel<EPI, BN, LORA>, dim3(2 * pairs), dim3(kThreads2), Cfg2<BN>::kSmem, stream, p));
   count_launch();
   return 0;
 }

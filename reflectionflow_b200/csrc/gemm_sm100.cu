@@ -158,6 +158,8 @@ gemm_kernel(const __grid_constant__ GemmParamsDev p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // PDL: the prologue above overlapped the previous kernel's tail
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -478,8 +480,7 @@ static int launch_cfg(const GemmParamsDev& p, cudaStream_t stream) {
   // algorithmic FLOPs: 2 M N K; algorithmic bytes: A + W + out once
   ProfScope prof(kNames[EPI], 2.0 * rows * p.N * p.K,
                  2.0 * (rows * p.K + static_cast<double>(p.ngroups) * p.N * p.K + rows * p.N), stream);
-  gemm_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
-  RF_CHECK_CUDA(cudaGetLastError());
+  RF_CHECK_CUDA(launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, p));
   count_launch();
   return 0;
 }

@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(kLdThreads, 1) lora_down_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     int stage = 0;
@@ -221,15 +223,15 @@ int lora_down_launch(const bf16* X, int ldx, int M, int K, const bf16* A, int NT
   switch (NT) {
     case 64:
       if ((rc = ld_set_attr<64>())) return rc;
-      lora_down_kernel<64><<<grid, kLdThreads, LdCfg<64>::kSmem, stream>>>(p);
+      RF_CHECK_CUDA(launch_pdl(lora_down_kernel<64>, dim3(grid), dim3(kLdThreads), LdCfg<64>::kSmem, stream, p));
       break;
     case 192:
       if ((rc = ld_set_attr<192>())) return rc;
-      lora_down_kernel<192><<<grid, kLdThreads, LdCfg<192>::kSmem, stream>>>(p);
+      RF_CHECK_CUDA(launch_pdl(lora_down_kernel<192>, dim3(grid), dim3(kLdThreads), LdCfg<192>::kSmem, stream, p));
       break;
     default:
       if ((rc = ld_set_attr<256>())) return rc;
-      lora_down_kernel<256><<<grid, kLdThreads, LdCfg<256>::kSmem, stream>>>(p);
+      RF_CHECK_CUDA(launch_pdl(lora_down_kernel<256>, dim3(grid), dim3(kLdThreads), LdCfg<256>::kSmem, stream, p));
       break;
   }
   RF_CHECK_CUDA(cudaGetLastError());

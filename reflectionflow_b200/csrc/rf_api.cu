@@ -1,3 +1,4 @@
+#include <cstdlib>
 // rf_api.cu — operator-level C ABI (include/rf_b200.h) over the kernel launchers.
 #include <atomic>
 #include <cstring>
@@ -8,6 +9,11 @@
 #include "rf_internal.h"
 
 namespace rf {
+bool pdl_enabled() {
+  static const bool on = !(getenv("RF_PDL") && getenv("RF_PDL")[0] == '0');
+  return on;
+}
+
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* get_error() { return g_err.c_str(); }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstring>
 #include <string>
 
 namespace rf {
@@ -27,6 +28,25 @@ int64_t launch_count();
       return -2;                                                                         \
     }                                                                                    \
   } while (0)
+
+// Launch with programmatic stream serialization (PDL) unless RF_PDL=0: the kernel MUST call
+// pdl_wait() (rf_ptx.cuh) before its first global-memory access.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Optional per-launch timing (rf_profile_start/stop): CUDA events around every kernel launch on
 // the launching stream, aggregated per kernel name with its algorithmic FLOPs / bytes.

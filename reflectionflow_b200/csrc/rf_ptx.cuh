@@ -303,6 +303,15 @@ __device__ __forceinline__ float2 gelu_tanh2(float2 x) {
 // ===================================================================== 2-CTA (cta_group::2) layer
 namespace rf {
 
+// ---- programmatic dependent launch (PDL): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its predecessor in the
+// stream is still draining; everything before pdl_wait() (barrier init, TMEM allocation, descriptor
+// prefetch) overlaps the predecessor's tail, and NO global memory may be touched before it.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
