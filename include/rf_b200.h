@@ -16,6 +16,7 @@
 #ifndef RF_B200_H_
 #define RF_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -51,6 +52,21 @@ int rf_op_linear(int epilogue, int M, int N, int K, const void* x, int ldx, cons
                  const void* bias, void* y, int ldy, const void* addend, int ld_addend,
                  const void* res, int ld_res, const void* gate, const float* rope_cos,
                  const float* rope_sin, const void* norm_q, const void* norm_k, void* stream);
+
+/* rf_op_linear with peft's unfused LoRA arithmetic fused in (condition-token call sites under
+ * enable_lora, train_flux/flux/lora_controller.py:5-42; targets train_flux/config.yaml:53):
+ *   y = epilogue( bf16( bf16(x W^T + b) + bf16( bf16(x lora_A^T) lora_B^T ) ) )
+ * lora_A: [t_cols, K] with t_cols = 64 (one target, rank zero-padded to 64) or 192 (stacked q|k|v A
+ * factors, RF_EPI_QKV); lora_B: [N, 64] (rank zero-padded).  M >= 128, N % 128 == 0, K % 64 == 0;
+ * epilogues GELU / GATE_RES / QKV.  workspace: rf_op_linear_lora_workspace_bytes(M) bytes of device
+ * memory, zero-initialised once by the caller (split-K partials, the bf16 down-projection and the
+ * reduction counters live there). */
+size_t rf_op_linear_lora_workspace_bytes(int M);
+int rf_op_linear_lora(int epilogue, int M, int N, int K, const void* x, int ldx, const void* W,
+                      const void* bias, void* y, int ldy, const void* lora_A, int t_cols,
+                      const void* lora_B, const void* res, int ld_res, const void* gate,
+                      const float* rope_cos, const float* rope_sin, const void* norm_q,
+                      const void* norm_k, void* workspace, void* stream);
 
 /* O = softmax(Q K^T / sqrt(128)) V, non-causal, head_dim 128, token-major operands
  * [batch*n_tok, heads*128] with row pitch ld_qkv / ld_out.  Replaces

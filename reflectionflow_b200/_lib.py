@@ -11,7 +11,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librf_b200.so")
+# RF_B200_LIB: load another build of the same library (kernel A/B experiments, tools/attn_ab.py)
+LIB_PATH = os.environ.get("RF_B200_LIB") or os.path.join(_HERE, "librf_b200.so")
 
 _lib = None
 
@@ -32,6 +33,11 @@ def _declare(lib):
     lib.rf_op_linear.restype = ci
     lib.rf_op_linear.argtypes = [ci, ci, ci, ci, vp, ci, vp, vp, vp, ci, vp, ci, vp, ci, vp, vp, vp,
                                  vp, vp, vp]
+    lib.rf_op_linear_lora_workspace_bytes.restype = ctypes.c_size_t
+    lib.rf_op_linear_lora_workspace_bytes.argtypes = [ci]
+    lib.rf_op_linear_lora.restype = ci
+    lib.rf_op_linear_lora.argtypes = [ci, ci, ci, ci, vp, ci, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, vp,
+                                      vp, vp, vp, vp]
     lib.rf_op_attention.restype = ci
     lib.rf_op_attention.argtypes = [vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, ci, cf, vp]
     lib.rf_op_ln_modulate.restype = ci

@@ -133,6 +133,50 @@ int rf_op_linear(int epilogue, int M, int N, int K, const void* x, int ldx, cons
   return rf::gemm_launch(epilogue, N, K, 1, &g, static_cast<cudaStream_t>(stream));
 }
 
+size_t rf_op_linear_lora_workspace_bytes(int M) {
+  const size_t rows = (static_cast<size_t>(M > 0 ? M : 1) + 127) / 128 * 128;
+  return ((rf::lora_down_workspace_bytes(M > 0 ? M : 1, 192) + 255) / 256) * 256 + rows * 192 * 2 + 256;
+}
+
+int rf_op_linear_lora(int epilogue, int M, int N, int K, const void* x, int ldx, const void* W,
+                      const void* bias, void* y, int ldy, const void* lora_A, int t_cols,
+                      const void* lora_B, const void* res, int ld_res, const void* gate,
+                      const float* rope_cos, const float* rope_sin, const void* norm_q,
+                      const void* norm_k, void* workspace, void* stream) {
+  if (!x || !W || !y || !lora_A || !lora_B || !workspace) {
+    rf::set_error("rf_op_linear_lora: null operand");
+    return -1;
+  }
+  if (t_cols != 64 && t_cols != 192) {
+    rf::set_error("rf_op_linear_lora: t_cols must be 64 (one target) or 192 (stacked q|k|v)");
+    return -1;
+  }
+  rf::GemmGroupArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = static_cast<const bf16*>(x); g.lda = ldx; g.M = M;
+  g.W = static_cast<const bf16*>(W);
+  g.bias = static_cast<const bf16*>(bias);
+  g.out = static_cast<bf16*>(y); g.ldo = ldy;
+  g.res = static_cast<const bf16*>(res); g.ldr = ld_res;
+  g.gate = static_cast<const bf16*>(gate);
+  g.rope_cos = rope_cos; g.rope_sin = rope_sin;
+  g.norm_q = static_cast<const bf16*>(norm_q);
+  g.norm_k = static_cast<const bf16*>(norm_k);
+  if (!rf::gemm2_lora_eligible(epilogue, N, K, g)) {
+    rf::set_error("rf_op_linear_lora: needs M >= 128, N % 128 == 0 (QKV: N % 384 == 0), K % 64 == 0, "
+                  "16-byte aligned pitches, and the GELU / GATE_RES / QKV epilogue");
+    return -1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // workspace = [split-K partials + counters | T (bf16 [rows, t_cols])]
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  bf16* T = reinterpret_cast<bf16*>(ws + ((rf::lora_down_workspace_bytes(M, 192) + 255) / 256) * 256);
+  int rc = rf::lora_down_launch(g.A, ldx, M, K, static_cast<const bf16*>(lora_A), t_cols, T, t_cols, ws, s);
+  if (rc) return rc;
+  return rf::gemm2_lora_launch(epilogue, N, K, g, T, t_cols, static_cast<const bf16*>(lora_B),
+                               t_cols == 192 ? N / 3 : 0, s);
+}
+
 int rf_op_attention(const void* q, const void* k, const void* v, int ld_qkv, void* out, int ld_out,
                     int n_tok, int heads, int batch, int n_main, int cond_mode, float cond_bias,
                     void* stream) {

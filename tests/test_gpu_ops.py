@@ -129,8 +129,12 @@ def _rope_tables(n_tok, seed=0):
 
 
 def _qkv_ref(x, W, b, cos, sin, nq, nk, heads):
-    M = x.shape[0]
-    y = _linear_ref(x, W, b)  # [M, 3*heads*128]
+    return _qkv_post_ref(_linear_ref(x, W, b), cos, sin, nq, nk, heads)
+
+
+def _qkv_post_ref(y, cos, sin, nq, nk, heads):
+    """per-head RMSNorm * w and interleaved RoPE on the q / k sections of a bf16 [M, 3*heads*128] linear output"""
+    M = y.shape[0]
     inner = heads * 128
     out = torch.empty_like(y)
     for sec, nw in ((0, nq), (1, nk)):
@@ -161,6 +165,107 @@ def test_linear_qkv_rmsnorm_rope(M, heads, K, gemm_path):
     _call_linear(3, x, W, b, y, cos=cos, sin=sin, nq=nq, nk=nk)
     ref = _qkv_ref(x, W, b, cos, sin, nq, nk, heads)
     _report("linear qkv", y, ref)
+    torch.testing.assert_close(y.float(), ref.float(), rtol=2 ** -6, atol=3e-2)
+
+
+def _lora_pad(A, B):
+    """rank r -> zero-padded rank 64 (the C ABI's LoRA layout)"""
+    r = A.shape[0]
+    Ap = torch.zeros(64, A.shape[1], dtype=A.dtype, device=A.device)
+    Bp = torch.zeros(B.shape[0], 64, dtype=B.dtype, device=B.device)
+    Ap[:r] = A
+    Bp[:, :r] = B
+    return Ap.contiguous(), Bp.contiguous()
+
+
+def _peft_linear_ref(x, W, b, A, B):
+    """peft LoRA Linear in bf16: base -> bf16, lora_A -> bf16, lora_B -> bf16, sum -> bf16"""
+    y = _linear_ref(x, W, b)
+    t = (x.float() @ A.float().t()).to(torch.bfloat16)
+    l = (t.float() @ B.float().t()).to(torch.bfloat16)
+    return (y.float() + l.float()).to(torch.bfloat16)
+
+
+def _call_linear_lora(epi, x, W, bias, y, Ap, Bp, t_cols, res=None, gate=None, cos=None, sin=None, nq=None,
+                      nk=None):
+    lib = L.load()
+    M, K = x.shape
+    N = W.shape[0]
+    ws = torch.zeros(lib.rf_op_linear_lora_workspace_bytes(M), dtype=torch.uint8, device=_dev())
+    for _ in range(2):  # twice: the in-kernel split-K counters must re-arm themselves
+        rc = lib.rf_op_linear_lora(epi, M, N, K, L.ptr(x), x.stride(0), L.ptr(W), L.ptr(bias), L.ptr(y), y.stride(0),
+                                   L.ptr(Ap), t_cols, L.ptr(Bp), L.ptr(res), res.stride(0) if res is not None else 0,
+                                   L.ptr(gate), L.ptr(cos), L.ptr(sin), L.ptr(nq), L.ptr(nk), L.ptr(ws), L.cur_stream())
+        L.check(rc, "rf_op_linear_lora")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 3072, 3072), (1024, 3072, 15360), (256, 256, 256), (1000, 1024, 12288)])
+def test_linear_lora_gate_res(M, N, K):
+    """fused peft-LoRA GEMM (split-K down-projection + low-rank k-block in the main GEMM) at the
+    headline condition-stream shapes: to_out / ff.net.2 / single proj_out (lora_controller.py:5-42)"""
+    x = _randn(M, K, seed=70)
+    W = _randn(N, K, scale=1.0 / math.sqrt(K), seed=71)
+    b = _randn(N, scale=0.1, seed=72)
+    A = _randn(32, K, scale=1.0 / math.sqrt(K), seed=73)
+    B = _randn(N, 32, scale=0.5 / math.sqrt(32), seed=74)
+    gate = _randn(N, scale=0.5, seed=75)
+    res = _randn(M, N, seed=76)
+    y = res.clone()
+    Ap, Bp = _lora_pad(A, B)
+    _call_linear_lora(2, x, W, b, y, Ap, Bp, 64, res=res.clone(), gate=gate)
+    lin = _peft_linear_ref(x, W, b, A, B)
+    ref = (res.float() + (gate.float()[None] * lin.float()).to(torch.bfloat16).float()).to(torch.bfloat16)
+    _report("linear_lora gate_res", y, ref)
+    torch.testing.assert_close(y.float(), ref.float(), rtol=2 ** -6, atol=3e-2)
+    assert (y == ref).float().mean().item() > 0.98
+
+
+def test_linear_lora_gelu():
+    M, N, K = 1024, 12288, 3072
+    x = _randn(M, K, seed=80)
+    W = _randn(N, K, scale=1.0 / math.sqrt(K), seed=81)
+    b = _randn(N, scale=0.1, seed=82)
+    A = _randn(32, K, scale=1.0 / math.sqrt(K), seed=83)
+    B = _randn(N, 32, scale=0.5 / math.sqrt(32), seed=84)
+    y = torch.empty((M, N), dtype=torch.bfloat16, device=_dev())
+    Ap, Bp = _lora_pad(A, B)
+    _call_linear_lora(1, x, W, b, y, Ap, Bp, 64)
+    lin = _peft_linear_ref(x, W, b, A, B)
+    ref = torch.nn.functional.gelu(lin.float(), approximate="tanh").to(torch.bfloat16)
+    _report("linear_lora gelu", y, ref)
+    torch.testing.assert_close(y.float(), ref.float(), rtol=2 ** -6, atol=3e-2)
+    assert (y == ref).float().mean().item() > 0.98
+
+
+@pytest.mark.parametrize("M,heads,K,only", [(1024, 24, 3072, None), (384, 2, 256, None), (1024, 2, 256, "k")])
+def test_linear_lora_qkv(M, heads, K, only):
+    """stacked q|k|v with per-section adapters (only="k": a k-only adapter — q and v get a zero term)"""
+    D = heads * 128
+    N = 3 * D
+    x = _randn(M, K, seed=90)
+    W = _randn(N, K, scale=1.0 / math.sqrt(K), seed=91)
+    b = _randn(N, scale=0.1, seed=92)
+    nq = (1.0 + 0.1 * _randn(128, seed=93).float()).to(torch.bfloat16)
+    nk = (1.0 + 0.1 * _randn(128, seed=94).float()).to(torch.bfloat16)
+    cos, sin = _rope_tables(M)
+    Ap = torch.zeros(192, K, dtype=torch.bfloat16, device=_dev())
+    Bp = torch.zeros(N, 64, dtype=torch.bfloat16, device=_dev())
+    lin = torch.empty((M, N), dtype=torch.bfloat16, device=_dev())
+    for j, nm in enumerate("qkv"):
+        Wj, bj = W[j * D:(j + 1) * D], b[j * D:(j + 1) * D]
+        if only is None or only == nm:
+            A = _randn(32, K, scale=1.0 / math.sqrt(K), seed=95 + j)
+            B = _randn(D, 32, scale=0.5 / math.sqrt(32), seed=98 + j)
+            Ap[64 * j:64 * j + 32] = A
+            Bp[j * D:(j + 1) * D, :32] = B
+            lin[:, j * D:(j + 1) * D] = _peft_linear_ref(x, Wj, bj, A, B)
+        else:
+            lin[:, j * D:(j + 1) * D] = _linear_ref(x, Wj, bj)
+    y = torch.empty((M, N), dtype=torch.bfloat16, device=_dev())
+    _call_linear_lora(3, x, W, b, y, Ap, Bp, 192, cos=cos, sin=sin, nq=nq, nk=nk)
+    ref = _qkv_post_ref(lin, cos, sin, nq, nk, heads)
+    _report("linear_lora qkv", y, ref)
     torch.testing.assert_close(y.float(), ref.float(), rtol=2 ** -6, atol=3e-2)
 
 
