@@ -122,6 +122,12 @@ struct AttnArgs {
 };
 int attention_launch(const AttnArgs& a, cudaStream_t stream);
 
+// T5 / CLIP self-attention, head_dim 64, S <= 512, on tcgen05 (text_attn_sm100.cu): eager-attention
+// rounding points (scores -> bf16 [* scale -> bf16] [+ bias -> bf16], fp32 softmax -> bf16, PV -> bf16)
+bool text_attn_tc_eligible(int S, int ld, int ldo);
+int text_attn_tc_launch(const bf16* q, const bf16* k, const bf16* v, int ld, bf16* out, int ldo, int B, int S,
+                        int heads, const bf16* bias, float scale, int use_scale, int causal, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------- bandwidth kernels
 // out = bf16(bf16(bf16(LN(x)) * bf16(1 + scale)) + shift)   (LN: no affine, eps 1e-6)
 //   rows of batch element b (= row / rows_per_batch) use scale/shift + b * mod_stride

@@ -350,6 +350,10 @@ int linear(int epi, const bf16* A, int lda, int M, const bf16* W, const bf16* bi
 }
 int small_attn(const bf16* q, const bf16* k, const bf16* v, int ld, bf16* out, int ldo, int B, int S, int heads,
                const bf16* bias, float scale, int use_scale, int causal, cudaStream_t s) {
+  // tensor-core path (text_attn_sm100.cu); RF_TEXT_ATTN=smem keeps the CUDA-core kernel below for A/B runs
+  static const bool force_smem = getenv("RF_TEXT_ATTN") && std::string(getenv("RF_TEXT_ATTN")) == "smem";
+  if (!force_smem && rf::text_attn_tc_eligible(S, ld, ldo))
+    return rf::text_attn_tc_launch(q, k, v, ld, out, ldo, B, S, heads, bias, scale, use_scale, causal, s);
   const size_t smem = static_cast<size_t>(8) * S * 16 + 8 * 64 * 16 + static_cast<size_t>(S) * 32 * 4 +
                       static_cast<size_t>(64) * rf::small_attn_sp2(S) * 4;
   static bool attr = false;
