@@ -183,9 +183,12 @@ static int ld_set_attr() {
 }
 int lora_down_init() { return (ld_set_attr<64>() | ld_set_attr<192>() | ld_set_attr<256>()) ? -2 : 0; }
 
+// layout: [counters: m_tiles x u32, padded to 256 B | partials].  The counters sit at a FIXED offset so that
+// launches with different NT sharing one workspace never overwrite each other's counters with partials.
+static size_t ld_counter_bytes(size_t m_tiles) { return (m_tiles * sizeof(unsigned) + 255) / 256 * 256; }
 size_t lora_down_workspace_bytes(int M, int NT) {
   const size_t m_tiles = (static_cast<size_t>(M) + 127) / 128;
-  return kLdMaxSplits * m_tiles * 128 * NT * sizeof(float) + m_tiles * sizeof(unsigned) + 256;
+  return ld_counter_bytes(m_tiles) + kLdMaxSplits * m_tiles * 128 * NT * sizeof(float);
 }
 
 // ws: lora_down_workspace_bytes(M, NT) bytes, ZERO-INITIALISED once by the caller (the counters live at
@@ -212,9 +215,9 @@ int lora_down_launch(const bf16* X, int ldx, int M, int K, const bf16* A, int NT
   p.kb_per = (p.num_kb + splits - 1) / splits;
   p.splits = (p.num_kb + p.kb_per - 1) / p.kb_per;  // every split non-empty
   const size_t rows_pad = static_cast<size_t>(p.m_tiles) * 128;
-  p.ws = static_cast<float*>(ws);
-  p.counters = reinterpret_cast<unsigned*>(static_cast<uint8_t*>(ws) +
-                                           kLdMaxSplits * rows_pad * NT * sizeof(float));
+  p.counters = static_cast<unsigned*>(ws);
+  p.ws = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + ld_counter_bytes(p.m_tiles));
+  (void)rows_pad;
   p.T = T;
   p.ldT = ldT;
   p.M = M;
