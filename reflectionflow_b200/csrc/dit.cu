@@ -249,7 +249,9 @@ int build_storage(rf_dit* h) {
     new_lora(h, ar, p + "norm.linear", b.l_norm, 3 * D, D);
     b.qkv = new_lin(h, ar, "", 3 * D, D);
     if (c.lora_rank > 0) {
-      b.qkvA = ar.take(static_cast<int64_t>(3 * kLoraPad) * D);
+      // A factors of to_q | to_k | to_v | proj_mlp stacked: all four read the same normalised tokens, so
+      // ONE down-projection launch (NT = 256) serves the q|k|v and the MLP-in GEMMs of the block
+      b.qkvA = ar.take(static_cast<int64_t>(4 * kLoraPad) * D);
       b.qkvB = ar.take(static_cast<int64_t>(3 * D) * kLoraPad);
     }
     const char* nm[3] = {"to_q", "to_k", "to_v"};
@@ -263,7 +265,8 @@ int build_storage(rf_dit* h) {
     b.norm_q = ar.take(128); reg(h, p + "attn.norm_q.weight", b.norm_q, 128);
     b.norm_k = ar.take(128); reg(h, p + "attn.norm_k.weight", b.norm_k, 128);
     b.mlp = new_lin(h, ar, p + "proj_mlp", 4 * D, D);
-    new_lora(h, ar, p + "proj_mlp", b.l_mlp, 4 * D, D);
+    new_lora(h, ar, p + "proj_mlp", b.l_mlp, 4 * D, D,
+             b.qkvA ? b.qkvA + static_cast<int64_t>(3 * kLoraPad) * D : nullptr);
     b.out = new_lin(h, ar, p + "proj_out", D, 5 * D);
     new_lora(h, ar, p + "proj_out", b.l_out, D, 5 * D);
   }
@@ -509,13 +512,20 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
   // T = bf16(x A^T) (one skinny GEMM), the other streams as one grouped launch, then the condition
   // stream with the low-rank k-block fused (gemm2_lora_launch) — L = T B^T never reaches HBM.  Small /
   // odd shapes keep the unfused path: L materialised by two GEMMs and added in the epilogue (`addend`).
+  // (t_pre != nullptr: T was already produced by an earlier launch, [M, ld_t] with this target's columns at t_pre)
   auto gemm_cond_lora = [&](int epi, int N, int K, int ngr, rf::GemmGroupArgs* gr, const bf16* loraA,
-                            int t_cols, const bf16* loraB, int sec_cols, auto&& unfused_term) -> int {
+                            int t_cols, const bf16* loraB, int sec_cols, auto&& unfused_term,
+                            const bf16* t_pre = nullptr, int ld_t = 0) -> int {
     rf::GemmGroupArgs& gc = gr[ngr - 1];
     if (rf::gemm2_lora_eligible(epi, N, K, gc)) {
-      RF_TRY(rf::lora_down_launch(gc.A, gc.lda, gc.M, K, loraA, t_cols, h->LT, t_cols, h->lora_ws, s));
+      const bf16* T = t_pre;
+      if (T == nullptr) {
+        RF_TRY(rf::lora_down_launch(gc.A, gc.lda, gc.M, K, loraA, t_cols, h->LT, t_cols, h->lora_ws, s));
+        T = h->LT;
+        ld_t = t_cols;
+      }
       if (ngr > 1) RF_TRY(rf::gemm_launch(epi, N, K, ngr - 1, gr, s));
-      return rf::gemm2_lora_launch(epi, N, K, gc, h->LT, t_cols, loraB, sec_cols, s);
+      return rf::gemm2_lora_launch(epi, N, K, gc, T, ld_t, loraB, sec_cols, s);
     }
     RF_TRY(unfused_term(gc));
     return rf::gemm_launch(epi, N, K, ngr, gr, s);
@@ -687,12 +697,18 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
       }
       ng = 2;
     }
+    // exact-mode fast path: T for to_q|to_k|to_v|proj_mlp in one launch (both GEMMs read the same XN rows)
+    const bool t4 = use_cond && !h->use_merged && (b.l_q.set || b.l_k.set || b.l_v.set) && b.l_mlp.set &&
+                    rf::gemm2_lora_eligible(rf::EPI_QKV, D3, D, g[ng - 1]);
+    if (t4)
+      RF_TRY(rf::lora_down_launch(g[ng - 1].A, D, S_cond.rows, D, b.qkvA, 4 * kLoraPad, h->LT, 4 * kLoraPad,
+                                  h->lora_ws, s));
     if (cond_lora) {
       RF_TRY(gemm_cond_lora(rf::EPI_QKV, D3, D, ng, g, b.qkvA, 3 * kLoraPad, b.qkvB, D, [&](rf::GemmGroupArgs& gc) {
         RF_TRY(lora_term_qkv(h, b.qkvA, b.l_q, b.l_k, b.l_v, gc.A, D, S_cond.rows, h->LL, D3, s));
         gc.addend = h->LL; gc.ldadd = D3;
         return 0;
-      }));
+      }, t4 ? h->LT : nullptr, 4 * kLoraPad));
     } else {
       RF_TRY(rf::gemm_launch(rf::EPI_QKV, D3, D, ng, g, s));
     }
@@ -718,7 +734,7 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
         RF_TRY(lora_term(h, b.l_mlp, gc.A, D, S_cond.rows, h->LL, D4, s));
         gc.addend = h->LL; gc.ldadd = D4;
         return 0;
-      }));
+      }, t4 ? h->LT + 3 * kLoraPad : nullptr, 4 * kLoraPad));
     } else {
       RF_TRY(rf::gemm_launch(rf::EPI_GELU, D4, D, ng, g, s));
     }
@@ -1055,10 +1071,10 @@ int rf_dit_prepare(rf_dit* h, int batch, int n_txt, int n_img, int n_cond, const
     if (!(p = A(static_cast<size_t>(h->n_mod) * 2))) return -2; h->MOD = static_cast<bf16*>(p);
     if (!(p = A(static_cast<size_t>(h->n_mod) * 2))) return -2; h->MODC = static_cast<bf16*>(p);
     const size_t lrows = static_cast<size_t>(std::max(n_cond, 1));
-    if (!(p = A(std::max(lrows * 3 * kLoraPad * 2, static_cast<size_t>(8 * D) * 2)))) return -2; h->LT = static_cast<bf16*>(p);
+    if (!(p = A(std::max(lrows * 4 * kLoraPad * 2, static_cast<size_t>(8 * D) * 2)))) return -2; h->LT = static_cast<bf16*>(p);
     if (!(p = A(std::max(lrows * 4 * D * 2, static_cast<size_t>(8 * D) * 2)))) return -2; h->LL = static_cast<bf16*>(p);
     {
-      const size_t wsb = rf::lora_down_workspace_bytes(std::max(n_cond, 1), 3 * kLoraPad);
+      const size_t wsb = rf::lora_down_workspace_bytes(std::max(n_cond, 1), 4 * kLoraPad);
       if (!(p = A(wsb))) return -2;
       h->lora_ws = p;
       RF_CHECK_CUDA(cudaMemsetAsync(p, 0, wsb, s));

@@ -7,8 +7,9 @@
 // fused into the condition stream's main GEMM (gemm2cta_sm100.cu, kLora).  The product is tiny
 // (M = 1024 condition tokens, NT <= 256) but K runs up to 15360: one CTA per 128-row tile would chain
 // 240 k-blocks on 8 SMs.  Here every (m tile, K split) pair is a CTA — tcgen05.mma 128 x NT x 16 from a
-// TMA ring, fp32 partial to a workspace — and the LAST CTA of an m tile to finish sums the partials in
-// split order (deterministic) and writes the bf16 rows.  One launch, no atomics on the data.
+// TMA ring, fp32 partial to a workspace — and once every split of an m tile has arrived each of its CTAs
+// sums a share of the rows over the partials in split order (deterministic) and writes the bf16 rows.
+// One launch, no atomics on the data.
 #include <cuda.h>
 
 #include "rf_internal.h"
@@ -23,7 +24,8 @@ static constexpr int kLdMaxSplits = 16;
 struct alignas(64) LoraDownParams {
   CUtensorMap tmX, tmA;
   float* ws;            // [splits][m_tiles * 128][NT] fp32 partials
-  unsigned* counters;   // [m_tiles], zero between launches (the last CTA re-arms its counter)
+  unsigned* counters;   // [m_tiles] arrivals, [m_tiles] finished shares: zero between launches (re-armed in-kernel)
+  unsigned* done;
   bf16* T;
   int ldT, M, num_kb, splits, kb_per, m_tiles;
 };
@@ -47,7 +49,6 @@ __global__ void __launch_bounds__(kLdThreads, 1) lora_down_kernel(const __grid_c
   uint64_t* empty_bar = full_bar + kLdStages;
   uint64_t* tfull_bar = empty_bar + kLdStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
-  uint32_t* last_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,39 +128,51 @@ __global__ void __launch_bounds__(kLdThreads, 1) lora_down_kernel(const __grid_c
         dst[q] = make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]),
                              __uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]));
     }
-    // ---- last CTA of this m tile reduces the splits in order (threadfence reduction pattern)
+    // ---- every split CTA of this m tile reduces its share of the rows once all partials are written.  All
+    // (m tile, split) CTAs are co-resident (grid <= one wave), so waiting on the arrival counter cannot
+    // deadlock; the partials are summed in split order (deterministic).
     __threadfence();
     named_bar_sync(2, 128);
     if (warp == 4 && lane == 0) {
-      const unsigned prev = atomicAdd(&p.counters[mt], 1u);
-      *last_flag = (prev == static_cast<unsigned>(p.splits - 1)) ? 1u : 0u;
+      atomicAdd(&p.counters[mt], 1u);
+      const volatile unsigned* cnt = p.counters + mt;
+      while (*cnt < static_cast<unsigned>(p.splits)) __nanosleep(32);
     }
     named_bar_sync(2, 128);
-    if (*last_flag != 0u) {
-      __threadfence();
-      if (row < p.M) {
-        bf16* trow = p.T + static_cast<size_t>(row) * p.ldT;
-#pragma unroll 1
-        for (int c = 0; c < NT / 8; ++c) {
-          float a[8];
+    __threadfence();
+    {
+      const int rps = (128 + p.splits - 1) / p.splits;  // rows per split CTA
+      const int r0 = sp * rps, r1 = min(128, r0 + rps);
+      const int items = (r1 - r0) * (NT / 8);           // (row, 8-column chunk) pairs
+      for (int it = r_in; it < items; it += 128) {
+        const int rr = r0 + it / (NT / 8), c = it % (NT / 8);
+        const int grow = mt * 128 + rr;
+        if (grow >= p.M) continue;
+        float a[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) a[i] = 0.f;
-          for (int s = 0; s < p.splits; ++s) {
-            const float4* src = reinterpret_cast<const float4*>(p.ws + (static_cast<size_t>(s) * rows_pad + row) * NT + c * 8);
-            const float4 u = __ldcg(src), v = __ldcg(src + 1);
-            a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
-            a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
-          }
-          uint4 o;
-          o.x = pack_bf16x2(a[0], a[1]);
-          o.y = pack_bf16x2(a[2], a[3]);
-          o.z = pack_bf16x2(a[4], a[5]);
-          o.w = pack_bf16x2(a[6], a[7]);
-          *reinterpret_cast<uint4*>(trow + c * 8) = o;
+        for (int i = 0; i < 8; ++i) a[i] = 0.f;
+        for (int s2 = 0; s2 < p.splits; ++s2) {
+          const float4* src = reinterpret_cast<const float4*>(p.ws + (static_cast<size_t>(s2) * rows_pad + grow) * NT + c * 8);
+          const float4 u = __ldcg(src), v = __ldcg(src + 1);
+          a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+          a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
         }
+        uint4 o;
+        o.x = pack_bf16x2(a[0], a[1]);
+        o.y = pack_bf16x2(a[2], a[3]);
+        o.z = pack_bf16x2(a[4], a[5]);
+        o.w = pack_bf16x2(a[6], a[7]);
+        *reinterpret_cast<uint4*>(p.T + static_cast<size_t>(grow) * p.ldT + c * 8) = o;
       }
-      named_bar_sync(2, 128);
-      if (warp == 4 && lane == 0) p.counters[mt] = 0u;  // re-arm for the next launch on this stream
+    }
+    // the last CTA to finish its share re-arms both counters (every CTA has left the wait loop by then)
+    named_bar_sync(2, 128);
+    if (warp == 4 && lane == 0) {
+      const unsigned prev = atomicAdd(&p.done[mt], 1u);
+      if (prev == static_cast<unsigned>(p.splits - 1)) {
+        p.counters[mt] = 0u;
+        p.done[mt] = 0u;
+      }
     }
   }
 
@@ -185,7 +198,7 @@ int lora_down_init() { return (ld_set_attr<64>() | ld_set_attr<192>() | ld_set_a
 
 // layout: [counters: m_tiles x u32, padded to 256 B | partials].  The counters sit at a FIXED offset so that
 // launches with different NT sharing one workspace never overwrite each other's counters with partials.
-static size_t ld_counter_bytes(size_t m_tiles) { return (m_tiles * sizeof(unsigned) + 255) / 256 * 256; }
+static size_t ld_counter_bytes(size_t m_tiles) { return (2 * m_tiles * sizeof(unsigned) + 255) / 256 * 256; }
 size_t lora_down_workspace_bytes(int M, int NT) {
   const size_t m_tiles = (static_cast<size_t>(M) + 127) / 128;
   return ld_counter_bytes(m_tiles) + kLdMaxSplits * m_tiles * 128 * NT * sizeof(float);
@@ -216,6 +229,7 @@ int lora_down_launch(const bf16* X, int ldx, int M, int K, const bf16* A, int NT
   p.splits = (p.num_kb + p.kb_per - 1) / p.kb_per;  // every split non-empty
   const size_t rows_pad = static_cast<size_t>(p.m_tiles) * 128;
   p.counters = static_cast<unsigned*>(ws);
+  p.done = p.counters + p.m_tiles;
   p.ws = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + ld_counter_bytes(p.m_tiles));
   (void)rows_pad;
   p.T = T;

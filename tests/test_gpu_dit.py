@@ -223,3 +223,23 @@ def test_k_only_adapter_is_applied():
     # closer to the adapted oracle than to the un-adapted one (bf16 noise ~1.3e-3, adapter effect ~4e-3)
     assert (out - ref).abs().mean() < 0.5 * (out - base).abs().mean()
     m.close()
+
+
+@pytest.mark.parametrize("name", ["fwdB_1024", "fwdB_full_c256"])
+def test_fused_lora_term_is_really_applied(name):
+    """>= 128 condition tokens take the fused-LoRA GEMMs (split-K down-projection + low-rank k-block).  The
+    error budget alone would not notice a missing low-rank term (its effect is about one bf16 error budget), so:
+    the CUDA output must be far closer to the reference WITH the adapter than to the oracle WITHOUT it."""
+    case = C.CASES[name]
+    gold, _ = _golden()
+    ours = _run_cuda(case).float()
+    with_lora = gold[name + "/bf16"].float()
+    model, _ = C.build_model(case)
+    x = C.build_inputs(case)
+    no_lora = fo.transformer_forward(model, x["latents"], x["prompt_embeds"], x["pooled"], x["timestep"],
+                                     x["img_ids"], x["txt_ids"], x["guidance"], x["cond_latents"], x["cond_ids"],
+                                     C.oracle_model_config(case), None).float()
+    d_with, d_without, effect = (ours - with_lora).abs().mean(), (ours - no_lora).abs().mean(), (with_lora - no_lora).abs().mean()
+    print(f"[{name}] |ours - ref(with LoRA)| {d_with:.4g} ; |ours - oracle(no LoRA)| {d_without:.4g} ; adapter effect {effect:.4g}")
+    assert effect > 2e-3, "the adapter must matter for this test to mean anything"
+    assert d_with < 0.6 * d_without

@@ -63,6 +63,8 @@ def test_selection_indices_match_the_oracle_loop(case_name, mode, rng_seed):
         err = max(abs(a - b) for a, b in zip(vals_o, vals_r))
         print(f"[{case_name} {mode} {vname}] topk_idx {idx_o}; min score gap {gap:.3g}, max |score err| {err:.3g}")
         assert idx_o == idx_r, f"selection differs: ours {idx_o} vs reference arithmetic {idx_r}"
-        if vname == "nvila":
-            assert [o["label"] for o in outs_o] == [o["label"] for o in outs_r]
+        if vname == "nvila":  # a yes/no label may only differ for a candidate sitting on the p = 0.5 boundary,
+            # where "yes, 0.5" and "no, 0.5" take the same place in the reference's sort key
+            for o, r, v in zip(outs_o, outs_r, vals_r):
+                assert o["label"] == r["label"] or abs(v) < 4 * err
         assert err < 0.25 * gap, "score error is not safely below the smallest gap between candidates"
