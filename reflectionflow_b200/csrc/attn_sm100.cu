@@ -38,11 +38,15 @@ struct alignas(64) AttnParamsDev {
   long long* trace;  // dev-only timeline of CTA 0 (rf_dbg_set_attn_trace); nullptr in production
 };
 
+#ifdef RF_DEV_HOOKS
 #define RF_TR(id, j)                                                                   \
   do {                                                                                 \
     if (p.trace != nullptr && blockIdx.x == 0 && (j) < 24 && (threadIdx.x & 31) == 0)  \
       p.trace[(j) * 16 + (id)] = clock64();                                            \
   } while (0)
+#else
+#define RF_TR(id, j) do { } while (0)
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

@@ -44,6 +44,8 @@ struct alignas(64) Gemm2Group {
   // a tile in column section s = n0 / lora_sec_cols reads T columns [64 s, 64 s + 64)
   CUtensorMap tmT, tmLB;
   int lora_sec_cols;
+  // per-group tile raster (kMix kernels: the LoRA group runs 256x128 tiles inside a launch of 256x256 tiles)
+  int bn, n_tiles, band, lora;
   const bf16* bias;
   const bf16* addend;
   const bf16* gate;
@@ -80,21 +82,22 @@ __device__ __forceinline__ Tile2 decode2(const Gemm2Params& p, int t) {
     if (i < p.ngroups && t >= p.g[i].tile_begin) g = i;
   const int local = t - p.g[g].tile_begin;
   const int mp = p.g[g].m_pairs;
-  const int full = p.n_tiles / p.band;
-  const int full_tiles = full * mp * p.band;
+  const int n_tiles = p.g[g].n_tiles, band = p.g[g].band;
+  const int full = n_tiles / band;
+  const int full_tiles = full * mp * band;
   int m, n;
   if (local < full_tiles) {
-    const int per = mp * p.band;
+    const int per = mp * band;
     const int sc = local / per, r = local - sc * per;
-    m = r / p.band;
-    n = sc * p.band + (r - m * p.band);
+    m = r / band;
+    n = sc * band + (r - m * band);
   } else {
-    const int rem = p.n_tiles - full * p.band;
+    const int rem = n_tiles - full * band;
     const int r = local - full_tiles;
     m = r / rem;
-    n = full * p.band + (r - m * rem);
+    n = full * band + (r - m * rem);
   }
-  return Tile2{g, m * 2 * kRows, n * p.bn};
+  return Tile2{g, m * 2 * kRows, n * p.g[g].bn};
 }
 
 __device__ __forceinline__ void ld8(const bf16* p, float* v) {  // 8 bf16 (16 B aligned) -> fp32
@@ -162,10 +165,14 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&acc)[64]) {
 // kLora (kBN == 128 only): the tile also accumulates L = T B^T (ONE extra 64-deep k-block, its own TMEM
 // accumulator: columns [2 kBN, 4 kBN)) and the epilogue forms bf16(bf16(acc + bias) + bf16(L)) — peft's
 // unfused LoRA arithmetic (lora_controller.py:5-42) without materialising L in HBM.
-template <int EPI, int kBN, bool kLora = false>
+// kMix (kBN == 256 only): groups flagged `lora` run 256 x 128 tiles whose base and low-rank accumulators share
+// ONE 256-column accumulator stage ([0, 128) base, [128, 256) L), so the condition stream rides in the same
+// persistent launch as the 256 x 256 tiles of the other streams (no extra launch, no tail of its own).
+template <int EPI, int kBN, bool kLora = false, bool kMix = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_kernel(const __grid_constant__ Gemm2Params p) {
   static_assert(!kLora || kBN == 128, "the LoRA accumulator needs the 128-wide tile (TMEM: 4 x 128 columns)");
+  static_assert(!kMix || (kBN == 256 && !kLora), "mixed tiles live in the 256-wide kernel");
   constexpr int kTmemCols = kLora ? 4 * kBN : 2 * kBN;
   constexpr int kStages = Cfg2<kBN>::kStages;
   constexpr int kStage = Cfg2<kBN>::kStage;
@@ -230,13 +237,16 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       const Tile2 tc = decode2(p, t);
       const Gemm2Group& G = p.g[tc.g];
       const int my_m = tc.m0 + rank * kRows;
-      const int my_n = tc.n0 + rank * (kBN / 2);
+      const int bnt = kMix ? G.bn : kBN;                         // this tile's width
+      const bool lora_tile = kLora || (kMix && G.lora != 0);
+      const uint32_t stage_tx = 2u * (kStageA + (bnt / 2) * kBK * 2);  // both CTAs: A rows + their half of W
+      const int my_n = tc.n0 + rank * (bnt / 2);
       PixTile pt{0, 0};
       if (G.conv_w != 0) pt = pix_tile(G, my_m);
-      if constexpr (kLora) {  // the low-rank k-block first: T rows of this CTA, B rows of its half tile
+      if (lora_tile) {  // the low-rank k-block first: T rows of this CTA, B rows of its half tile
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * kStage;
-        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStage);
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
         const int tcol = G.lora_sec_cols > 0 ? (tc.n0 / G.lora_sec_cols) * 64 : 0;
         tma_load_2d_2cta(sa, &G.tmT, &full_bar[stage], tcol, my_m);
         tma_load_2d_2cta(sa + kStageA, &G.tmLB, &full_bar[stage], 0, my_n);
@@ -250,7 +260,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         if (p.dbg_skip == 2) {
         } else
 #else
-        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStage);
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
 #endif
         if (G.conv_w != 0) {
           const int tap = kb / G.conv_cin_blocks;
@@ -285,7 +295,11 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kBN;
       long long stall = 0;
-      if constexpr (kLora) {
+      const Gemm2Group& GM = p.g[decode2(p, t).g];
+      const bool lora_tile = kLora || (kMix && GM.lora != 0);
+      const uint32_t idesc_t = kMix ? make_idesc_bf16(256, static_cast<uint32_t>(GM.bn), 0, 0) : idesc;
+      const uint32_t l_off = kMix ? 128u : 2u * kBN;  // column offset of the low-rank accumulator
+      if (lora_tile) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * kStage);
@@ -293,7 +307,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         const uint64_t bdesc = make_smem_desc(sa + kStageA, 16, 1024, 2);
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k)
-          mma_ss_2cta(d_tmem + 2 * kBN, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
+          mma_ss_2cta(d_tmem + l_off, adesc + 2 * k, bdesc + 2 * k, idesc_t, k != 0 ? 1u : 0u);
         tc_commit_2cta(&empty_bar[stage], 3);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -311,7 +325,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         const uint64_t bdesc = make_smem_desc(sa + kStageA, 16, 1024, 2);
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k)
-          mma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          mma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_t, (kb | k) != 0 ? 1u : 0u);
         tc_commit_2cta(&empty_bar[stage], 3);  // slot free in both CTAs
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -354,11 +368,15 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       if (etr && eti < 16) p.trace[eti * 8 + 4] = clock64();
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_off + as * kBN;
+      const int bnt = kMix ? G.bn : kBN;
+      const bool lora_tile = kLora || (kMix && G.lora != 0);
+      const uint32_t l_off = kMix ? 128u : 2u * kBN;
       // v = bf16(v + bf16(L)): the low-rank term of this 64-column chunk from its own accumulator
       auto lora_add = [&](uint32_t col, float (&v)[64]) {
-        if constexpr (kLora) {
+        if constexpr (kLora || kMix) {
+          if (!lora_tile) return;
           uint32_t accl[64];
-          tmem_ld64(taddr + 2 * kBN + col, accl);
+          tmem_ld64(taddr + l_off + col, accl);
 #pragma unroll
           for (int i = 0; i < 64; i += 2) {
             float l0 = __uint_as_float(accl[i]), l1 = __uint_as_float(accl[i + 1]);
@@ -395,7 +413,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         const float* cosr = G.rope_cos + static_cast<size_t>(row_c) * 64;
         const float* sinr = G.rope_sin + static_cast<size_t>(row_c) * 64;
 #pragma unroll 1
-        for (int hc = 0; hc < kBN / 128; ++hc) {
+        for (int hc = 0; hc < bnt / 128; ++hc) {
           const int col_h = tc.n0 + hc * 128;
           const int section = col_h / inner;  // 0 q, 1 k, 2 v
           const bf16* bias_h = G.bias ? G.bias + col_h : nullptr;
@@ -463,14 +481,14 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       } else {
         const bf16* add_r = G.addend ? G.addend + static_cast<size_t>(row_c) * G.ldadd + tc.n0 : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < kBN / 64; ++c) {
+        for (int c = 0; c < bnt / 64; ++c) {
           float r[64];
           if constexpr (EPI == EPI_GATE_RES) {
             // prefetch the residual of the NEXT chunk into the other box (everybody finished reading
             // it before the barriers inside publish() of the previous chunk)
             if (issuer) {
               int nt = t, nc = c + 1;
-              if (nc == kBN / 64) { nt = t + npairs; nc = 0; }
+              if (nc == bnt / 64) { nt = t + npairs; nc = 0; }
               if (nt < p.total_tiles) {
                 const Tile2 tn = decode2(p, nt);
                 const uint32_t nb = (cc + 1) & 1;
@@ -539,11 +557,11 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
 }
 
 // ------------------------------------------------------------------------------------ host
-template <int EPI, int BN, bool LORA = false>
+template <int EPI, int BN, bool LORA = false, bool MIX = false>
 static int set_attr2() {
   static bool done = false;
   if (!done) {
-    RF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI, BN, LORA>,
+    RF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI, BN, LORA, MIX>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmem));
     done = true;
   }
@@ -553,13 +571,14 @@ int gemm2_init() {
   return (set_attr2<EPI_BIAS, 256>() | set_attr2<EPI_GELU, 256>() | set_attr2<EPI_GATE_RES, 256>() |
           set_attr2<EPI_QKV, 256>() | set_attr2<EPI_BIAS, 128>() | set_attr2<EPI_GATE_RES, 128>() |
           set_attr2<EPI_GELU, 128, true>() | set_attr2<EPI_GATE_RES, 128, true>() |
-          set_attr2<EPI_QKV, 128, true>())
+          set_attr2<EPI_QKV, 128, true>() | set_attr2<EPI_GELU, 256, false, true>() |
+          set_attr2<EPI_GATE_RES, 256, false, true>() | set_attr2<EPI_QKV, 256, false, true>())
              ? -2
              : 0;
 }
 
 long long* dbg_get_gemm_trace();
-template <int EPI, int BN, bool LORA = false>
+template <int EPI, int BN, bool LORA = false, bool MIX = false>
 static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t stream) {
   Gemm2Params p = p_in;
   p.trace = dbg_get_gemm_trace();
@@ -569,14 +588,14 @@ static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t
     p.dbg_skip = skip;
   }
 #endif
-  if (int rc = set_attr2<EPI, BN, LORA>()) return rc;
+  if (int rc = set_attr2<EPI, BN, LORA, MIX>()) return rc;
   static const char* kNames[4] = {"gemm_bias", "gemm_gelu", "gemm_gate_res", "gemm_qkv_rms_rope"};
   const char* name = p.g[0].conv_w ? (EPI == EPI_GATE_RES ? "conv_res" : "conv_bias") : kNames[EPI];
   ProfScope prof(name, 2.0 * rows * p.N * p.K,
                  2.0 * (rows * p.K / (p.g[0].conv_w ? p.g[0].conv_taps : 1) +
                         static_cast<double>(p.ngroups) * p.N * p.K + rows * p.N),
                  stream);
-  RF_CHECK_CUDA(launch_pdl(gemm2_kernel<EPI, BN, LORA>, dim3(2 * pairs), dim3(kThreads2), Cfg2<BN>::kSmem, stream, p));
+  RF_CHECK_CUDA(launch_pdl(gemm2_kernel<EPI, BN, LORA, MIX>, dim3(2 * pairs), dim3(kThreads2), Cfg2<BN>::kSmem, stream, p));
   count_launch();
   return 0;
 }
@@ -667,11 +686,90 @@ int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups
     d.rope_cos = a.rope_cos; d.rope_sin = a.rope_sin; d.norm_q = a.norm_q; d.norm_k = a.norm_k;
     d.M = a.M; d.ldadd = a.ldadd;
     d.m_pairs = (a.M + 2 * kRows - 1) / (2 * kRows);
+    d.bn = p.bn; d.n_tiles = p.n_tiles; d.band = p.band; d.lora = 0;
     d.tile_begin = tiles;
     tiles += d.m_pairs * p.n_tiles;
     rows += a.M;
   }
   return gemm2_dispatch(epi, p, tiles, rows, stream);
+}
+
+// Grouped launch whose LAST group (the condition stream) carries a fused peft LoRA: its tiles are 256 x 128
+// with the low-rank accumulator in the second half of the accumulator stage; the other groups keep the
+// 256 x 256 tiles.  T / loraB / sec_cols as in gemm2_lora_launch.
+bool gemm2_mixed_eligible(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups) {
+  if (ngroups < 2 || !gemm2_eligible(epi, N, K, ngroups, groups)) return false;
+  return gemm2_lora_eligible(epi, N, K, groups[ngroups - 1]);
+}
+int gemm2_mixed_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups, const bf16* T, int ldT,
+                       const bf16* loraB, int sec_cols, cudaStream_t stream) {
+  Gemm2Params p;
+  memset(&p, 0, sizeof(p));
+  p.ngroups = ngroups;
+  p.N = N;
+  p.K = K;
+  p.bn = 256;
+  p.n_tiles = N / 256;
+  p.num_kb = K / kBK;
+  p.band = p.n_tiles <= 12 ? p.n_tiles : 4;
+  int tiles = 0;
+  double rows = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    const GemmGroupArgs& a = groups[g];
+    Gemm2Group& d = p.g[g];
+    const bool lora = g == ngroups - 1;
+    d.bn = lora ? 128 : 256;
+    d.n_tiles = N / d.bn;
+    d.band = lora ? (d.n_tiles <= 24 ? d.n_tiles : 8) : p.band;
+    d.lora = lora ? 1 : 0;
+    int rc = make_tmap_2d(&d.tmA, a.A, a.M, K, a.lda, kRows);
+    if (rc) return rc;
+    rc = make_tmap_2d(&d.tmB, a.W, N, K, K, d.bn / 2);
+    if (rc) return rc;
+    rc = make_tmap_2d(&d.tmOut, a.out, a.M, N, a.ldo, kRows);
+    if (rc) return rc;
+    if (epi == EPI_GATE_RES) {
+      if (a.res == nullptr || a.gate == nullptr) {
+        set_error("gemm2_mixed_launch: EPI_GATE_RES needs res and gate");
+        return -1;
+      }
+      rc = make_tmap_2d(&d.tmRes, a.res, a.M, N, a.ldr, kRows);
+      if (rc) return rc;
+    }
+    if (epi == EPI_QKV && (!a.rope_cos || !a.rope_sin || !a.norm_q || !a.norm_k)) {
+      set_error("gemm2_mixed_launch: EPI_QKV needs rope tables and norm weights");
+      return -1;
+    }
+    if (lora) {
+      const int t_cols = sec_cols > 0 ? (N / sec_cols) * 64 : 64;
+      rc = make_tmap_2d(&d.tmT, T, a.M, t_cols, ldT, kRows);
+      if (rc) return rc;
+      rc = make_tmap_2d(&d.tmLB, loraB, N, 64, 64, d.bn / 2);
+      if (rc) return rc;
+      d.lora_sec_cols = sec_cols;
+    }
+    d.bias = a.bias; d.addend = lora ? nullptr : a.addend; d.gate = a.gate;
+    d.rope_cos = a.rope_cos; d.rope_sin = a.rope_sin; d.norm_q = a.norm_q; d.norm_k = a.norm_k;
+    d.M = a.M; d.ldadd = a.ldadd;
+    d.m_pairs = (a.M + 2 * kRows - 1) / (2 * kRows);
+    d.tile_begin = tiles;
+    tiles += d.m_pairs * d.n_tiles;
+    rows += a.M;
+  }
+  p.total_tiles = tiles;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int pairs = sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  switch (epi) {
+    case EPI_GELU: return launch2<EPI_GELU, 256, false, true>(p, pairs, rows, stream);
+    case EPI_GATE_RES: return launch2<EPI_GATE_RES, 256, false, true>(p, pairs, rows, stream);
+    case EPI_QKV: return launch2<EPI_QKV, 256, false, true>(p, pairs, rows, stream);
+    default: break;
+  }
+  set_error("gemm2_mixed_launch: unsupported epilogue");
+  return -1;
 }
 
 // One token stream (the condition tokens) with peft LoRA fused: out = epi(bf16(bf16(A W^T + b) + bf16(T B^T))),
@@ -725,6 +823,7 @@ int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16*
   d.M = a.M; d.ldadd = 0;
   d.lora_sec_cols = sec_cols;
   d.m_pairs = (a.M + 2 * kRows - 1) / (2 * kRows);
+  d.bn = p.bn; d.n_tiles = p.n_tiles; d.band = p.band; d.lora = 1;
   d.tile_begin = 0;
   const int tiles = d.m_pairs * p.n_tiles;
   p.total_tiles = tiles;
@@ -785,6 +884,7 @@ int conv_launch(const bf16* in, const bf16* weight, const bf16* bias, bf16* out,
   d.gate = ones;  // residual epilogue = bf16(res + bf16(1 * y))
   d.M = H * W;
   d.m_pairs = (d.M + 2 * kRows - 1) / (2 * kRows);
+  d.bn = p.bn; d.n_tiles = p.n_tiles; d.band = p.band; d.lora = 0;
   d.conv_w = W;
   d.conv_taps = taps;
   d.conv_cin_blocks = Cin / kBK;
