@@ -25,7 +25,7 @@ static constexpr int kTile = 128;
 static constexpr int kHalfBytes = kTile * 128;   // one [128 x 64] bf16 box = 16 KB
 static constexpr int kTileBytes = 2 * kHalfBytes;  // [128 x 128] bf16 = 32 KB
 static constexpr int kKVStages = 2;
-static constexpr int kPolyEvery = 2;  // every n-th exp2 pair on the FMA pipe (0 = all on MUFU)
+static constexpr int kPolyEvery = 4;  // every n-th exp2 pair on the FMA pipe (0 = all on MUFU)
 static constexpr int kAttnSmem = (2 + 2 * kKVStages) * kTileBytes + 1024 + 256;
 
 struct alignas(64) AttnParamsDev {

@@ -162,18 +162,24 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&acc)[64]) {
   tmem_ld_wait();
 }
 
-// kLora (kBN == 128 only): the tile also accumulates L = T B^T (ONE extra 64-deep k-block, its own TMEM
-// accumulator: columns [2 kBN, 4 kBN)) and the epilogue forms bf16(bf16(acc + bias) + bf16(L)) — peft's
-// unfused LoRA arithmetic (lora_controller.py:5-42) without materialising L in HBM.
+// kLora: the tile also accumulates L = T B^T (ONE extra 64-deep k-block, its own TMEM accumulator) and the
+// epilogue forms bf16(bf16(acc + bias) + bf16(L)) — peft's unfused LoRA arithmetic (lora_controller.py:5-42)
+// without materialising L in HBM.  kBN = 128: two accumulator stages of (128 base + 128 L); kBN = 256: one stage
+// of (256 base + 256 L) — these launches are bound by L2 -> SM operand traffic, and the 256-wide tile needs a
+// third less of it per FLOP (ncu, K = 15360 condition stream: 141 us at 128 wide).
 // kMix (kBN == 256 only): groups flagged `lora` run 256 x 128 tiles whose base and low-rank accumulators share
 // ONE 256-column accumulator stage ([0, 128) base, [128, 256) L), so the condition stream rides in the same
 // persistent launch as the 256 x 256 tiles of the other streams (no extra launch, no tail of its own).
 template <int EPI, int kBN, bool kLora = false, bool kMix = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_kernel(const __grid_constant__ Gemm2Params p) {
-  static_assert(!kLora || kBN == 128, "the LoRA accumulator needs the 128-wide tile (TMEM: 4 x 128 columns)");
   static_assert(!kMix || (kBN == 256 && !kLora), "mixed tiles live in the 256-wide kernel");
-  constexpr int kTmemCols = kLora ? 4 * kBN : 2 * kBN;
+  // TMEM: kLora/128: 2 stages x (128 base + 128 L); kLora/256: ONE stage of 256 base + 256 L (the 256-wide tile
+  // halves the L2 traffic per FLOP of the 128-wide one, which is what bounds these launches; the price is
+  // that a tile's epilogue no longer overlaps the next mainloop); otherwise 2 stages x kBN
+  constexpr int kAccStages = (kLora && kBN == 256) ? 1 : 2;
+  constexpr int kTmemCols = kLora ? 512 : 2 * kBN;
+  constexpr uint32_t kLoraOff = (kBN == 256) ? 256u : 2u * kBN;  // column offset of the low-rank accumulator
   constexpr int kStages = Cfg2<kBN>::kStages;
   constexpr int kStage = Cfg2<kBN>::kStage;
   extern __shared__ uint8_t smem_raw[];
@@ -298,7 +304,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       const Gemm2Group& GM = p.g[decode2(p, t).g];
       const bool lora_tile = kLora || (kMix && GM.lora != 0);
       const uint32_t idesc_t = kMix ? make_idesc_bf16(256, static_cast<uint32_t>(GM.bn), 0, 0) : idesc;
-      const uint32_t l_off = kMix ? 128u : 2u * kBN;  // column offset of the low-rank accumulator
+      const uint32_t l_off = kMix ? 128u : kLoraOff;  // column offset of the low-rank accumulator
       if (lora_tile) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -331,7 +337,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       }
       tc_commit_2cta(&tfull_bar[as], 3);  // accumulator complete in both CTAs
       if (tr && ti < 16) { p.trace[ti * 8 + 2] = stall; p.trace[ti * 8 + 3] = clock64(); }
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == kAccStages) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs) =====================
@@ -370,7 +376,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       const uint32_t taddr = tmem_base + lane_off + as * kBN;
       const int bnt = kMix ? G.bn : kBN;
       const bool lora_tile = kLora || (kMix && G.lora != 0);
-      const uint32_t l_off = kMix ? 128u : 2u * kBN;
+      const uint32_t l_off = kMix ? 128u : kLoraOff;
       // v = bf16(v + bf16(L)): the low-rank term of this 64-column chunk from its own accumulator
       auto lora_add = [&](uint32_t col, float (&v)[64]) {
         if constexpr (kLora || kMix) {
@@ -543,7 +549,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
       if (etr && eti < 16) p.trace[eti * 8 + 5] = clock64();
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == kAccStages) { as = 0; aphase ^= 1; }
     }
     if (issuer) tma_store_wait_all<0>();  // all boxes written to global before the kernel ends
   }
@@ -571,7 +577,8 @@ int gemm2_init() {
   return (set_attr2<EPI_BIAS, 256>() | set_attr2<EPI_GELU, 256>() | set_attr2<EPI_GATE_RES, 256>() |
           set_attr2<EPI_QKV, 256>() | set_attr2<EPI_BIAS, 128>() | set_attr2<EPI_GATE_RES, 128>() |
           set_attr2<EPI_GELU, 128, true>() | set_attr2<EPI_GATE_RES, 128, true>() |
-          set_attr2<EPI_QKV, 128, true>() | set_attr2<EPI_GELU, 256, false, true>() |
+          set_attr2<EPI_QKV, 128, true>() | set_attr2<EPI_GELU, 256, true>() | set_attr2<EPI_GATE_RES, 256, true>() |
+          set_attr2<EPI_QKV, 256, true>() | set_attr2<EPI_GELU, 256, false, true>() |
           set_attr2<EPI_GATE_RES, 256, false, true>() | set_attr2<EPI_QKV, 256, false, true>())
              ? -2
              : 0;
@@ -790,10 +797,13 @@ int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16*
   p.ngroups = 1;
   p.N = N;
   p.K = K;
-  p.bn = 128;
+  // 256-wide tiles (single accumulator stage) unless N only divides by 128 or RF_LORA_BN=128 asks for the
+  // double-buffered 128-wide form (A/B runs)
+  const char* bnenv = getenv("RF_LORA_BN");
+  p.bn = (N % 256 == 0 && !(bnenv && atoi(bnenv) == 128)) ? 256 : 128;
   p.n_tiles = N / p.bn;
   p.num_kb = K / kBK;
-  p.band = p.n_tiles <= 24 ? p.n_tiles : 8;  // same W-slice footprint per band as the 256-wide raster
+  p.band = p.bn == 256 ? (p.n_tiles <= 12 ? p.n_tiles : 4) : (p.n_tiles <= 24 ? p.n_tiles : 8);
   Gemm2Group& d = p.g[0];
   int rc = make_tmap_2d(&d.tmA, a.A, a.M, K, a.lda, kRows);
   if (rc) return rc;
@@ -832,11 +842,20 @@ int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16*
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;
-  switch (epi) {
-    case EPI_GELU: return launch2<EPI_GELU, 128, true>(p, pairs, a.M, stream);
-    case EPI_GATE_RES: return launch2<EPI_GATE_RES, 128, true>(p, pairs, a.M, stream);
-    case EPI_QKV: return launch2<EPI_QKV, 128, true>(p, pairs, a.M, stream);
-    default: break;
+  if (p.bn == 256) {
+    switch (epi) {
+      case EPI_GELU: return launch2<EPI_GELU, 256, true>(p, pairs, a.M, stream);
+      case EPI_GATE_RES: return launch2<EPI_GATE_RES, 256, true>(p, pairs, a.M, stream);
+      case EPI_QKV: return launch2<EPI_QKV, 256, true>(p, pairs, a.M, stream);
+      default: break;
+    }
+  } else {
+    switch (epi) {
+      case EPI_GELU: return launch2<EPI_GELU, 128, true>(p, pairs, a.M, stream);
+      case EPI_GATE_RES: return launch2<EPI_GATE_RES, 128, true>(p, pairs, a.M, stream);
+      case EPI_QKV: return launch2<EPI_QKV, 128, true>(p, pairs, a.M, stream);
+      default: break;
+    }
   }
   set_error("gemm2_lora_launch: unsupported epilogue");
   return -1;

@@ -24,6 +24,7 @@ cfg["pipeline_args"]["num_inference_steps"] = steps
 class A:
     synthetic, layers_ = True, layers
 A.layers = layers
+A.lora_mode = os.environ.get("LORA_MODE", "exact")
 A.text_encoders = os.environ.get("TEXT", "native")  # T5-XXL + CLIP-L of every candidate prompt run on the device
 pipe = RF.build_pipeline(cfg, A, ctx)
 torch.manual_seed(0)
@@ -76,7 +77,7 @@ if ctx.world > 1:
 n_steps = steps * branch * rounds
 if ctx.rank == 0:
     print(json.dumps({"workload": f"{steps}-step x {branch}-cand x {rounds}-round reflection tree, 1024x1024, cond 512x512, "
-                                  "merged LoRA, VAE decode+resize+encode per parent, PNG+latent artefacts written, text encoders: " + A.text_encoders,
+                                  f"LoRA {A.lora_mode}, " "VAE decode+resize+encode per parent, PNG+latent artefacts written, text encoders: " + A.text_encoders,
                       "n_gpus": ctx.world, "layers": layers, "denoise_steps": n_steps, "images": branch * rounds,
                       "seconds": ms / 1e3, "wall_seconds": wall, "denoise_steps_per_s": n_steps / (ms / 1e3),
                       "images_per_s": branch * rounds / (ms / 1e3),

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """dev tool: in-process A/B of the LoRA arithmetic / launch forms on the headline step (5632 tokens):
-exact with the condition stream as its own launch, exact with mixed tiles (RF_LORA_MIX=1), merged — alternated
+exact with 256-wide (single accumulator stage) / 128-wide (double-buffered) condition tiles, merged — alternated
 several times in ONE process so that box / clock state is shared."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -37,8 +37,8 @@ lora = RF.synthetic_lora(m.cfg, seed=1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
-def run(mode, mix):
-    os.environ["RF_LORA_MIX"] = "1" if mix else "0"
+def run(mode, bn):
+    os.environ["RF_LORA_BN"] = str(bn)  # condition-stream tile width of the fused-LoRA GEMM (read at capture time)
     m.load_lora(lora, mode=mode)   # drops the captured graph: the next denoise re-captures with this form
     m.denoise(lat, txt, pool, t_in[:3], sig[:4], 3.5, img_ids, txt_ids, cond, cond_ids, {})
     torch.cuda.synchronize()
@@ -49,9 +49,9 @@ def run(mode, mix):
     return e0.elapsed_time(e1) / K
 
 
-res = {"exact_split": [], "exact_mix": [], "merged": []}
+res = {"exact_bn256": [], "exact_bn128": [], "merged": []}
 for rep in range(3):
-    res["exact_split"].append(run("exact", False))
-    res["exact_mix"].append(run("exact", True))
-    res["merged"].append(run("merged", False))
+    res["exact_bn256"].append(run("exact", 256))
+    res["exact_bn128"].append(run("exact", 128))
+    res["merged"].append(run("merged", 256))
 print(json.dumps({k: [round(x, 2) for x in v] for k, v in res.items()}))

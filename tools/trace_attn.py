@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""dev tool: clock64 timeline of CTA 0 of the attention kernel (MMA thread + one lane per softmax WG)."""
+"""dev tool: clock64 timeline of CTA 0 of the attention kernel (MMA thread + one lane per softmax WG).
+Needs a DEV build (`make -C reflectionflow_b200/csrc clean all DEV=1`): the probes are compiled out of production
+builds (they cost ~12 % of the softmax loop's instructions)."""
 import os, sys, ctypes
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
