@@ -6,8 +6,10 @@ mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 1 --no-tree --no-eager --no-cpu-baseline --no-text"
 # warm-up step + e2e etc. come later in bench.py; the first ~450 launches after pipeline build are the warm-up step,
 # the next ~900 the two timed steps: capture a window that covers them
+# (only this library's kernels: the synthetic-weight initialisation launches thousands of torch kernels first)
+KN='regex:^(gemm2_kernel|gemm_kernel|attn_kernel|ln_modulate_kernel|lora_down_kernel|gemv_kernel|select_row_kernel|euler_step_kernel|advance_step_kernel|add2_kernel|add3_kernel|timestep_embed_kernel|f32_to_bf16_kernel)$'
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -s 200 -c 1400 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/r02_launches.log 2>&1
+    -k "$KN" -c 1800 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/r02_launches.log 2>&1
 echo "launch list rc=$?"
 # full captures: attention (entry-B geometry), the mixed LoRA gate+res GEMM, the LoRA down-projection
 ncu --set full --clock-control none --import-source on -k regex:attn_kernel -s 60 -c 2 \
