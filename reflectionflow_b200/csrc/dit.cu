@@ -525,12 +525,6 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
         T = h->LT;
         ld_t = t_cols;
       }
-      // RF_LORA_MIX=1 (read at capture time): one persistent launch for all streams, the condition tiles
-      // 256 x 128 with the low-rank accumulator in the second half of the accumulator stage; default: the
-      // condition stream as its own launch (measured equal within noise, profiles/r02_summary.md)
-      const char* mixenv = getenv("RF_LORA_MIX");
-      if (mixenv && mixenv[0] == '1' && rf::gemm2_mixed_eligible(epi, N, K, ngr, gr))
-        return rf::gemm2_mixed_launch(epi, N, K, ngr, gr, T, ld_t, loraB, sec_cols, s);
       if (ngr > 1) RF_TRY(rf::gemm_launch(epi, N, K, ngr - 1, gr, s));
       return rf::gemm2_lora_launch(epi, N, K, gc, T, ld_t, loraB, sec_cols, s);
     }

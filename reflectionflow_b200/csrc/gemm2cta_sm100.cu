@@ -44,7 +44,7 @@ struct alignas(64) Gemm2Group {
   // a tile in column section s = n0 / lora_sec_cols reads T columns [64 s, 64 s + 64)
   CUtensorMap tmT, tmLB;
   int lora_sec_cols;
-  // per-group tile raster (kMix kernels: the LoRA group runs 256x128 tiles inside a launch of 256x256 tiles)
+  // per-group tile raster
   int bn, n_tiles, band, lora;
   const bf16* bias;
   const bf16* addend;
@@ -167,13 +167,15 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&acc)[64]) {
 // without materialising L in HBM.  kBN = 128: two accumulator stages of (128 base + 128 L); kBN = 256: one stage
 // of (256 base + 256 L) — these launches are bound by L2 -> SM operand traffic, and the 256-wide tile needs a
 // third less of it per FLOP (ncu, K = 15360 condition stream: 141 us at 128 wide).
-// kMix (kBN == 256 only): groups flagged `lora` run 256 x 128 tiles whose base and low-rank accumulators share
-// ONE 256-column accumulator stage ([0, 128) base, [128, 256) L), so the condition stream rides in the same
-// persistent launch as the 256 x 256 tiles of the other streams (no extra launch, no tail of its own).
-template <int EPI, int kBN, bool kLora = false, bool kMix = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+// kEG = 2 (kBN == 256): TWO epilogue warpgroups (warps 4..7 and 8..11, 384 threads).  A TMEM lane quadrant can
+// only be read by warps of one SM sub-partition, so with one warpgroup every scheduler sees a single epilogue
+// warp and nothing hides its dependent-issue latency: the K = 3072 GEMMs were epilogue-bound (30-35 k cycles per
+// tile against a 27 k mainloop).  Group g owns columns [128 g, 128 g + 128) of every tile (one attention head of
+// the QKV epilogue) with its own staging box, residual box and named barrier.
+template <int EPI, int kBN, bool kLora = false, int kEG = 1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2 + 128 * (kEG - 1), 1)
 gemm2_kernel(const __grid_constant__ Gemm2Params p) {
-  static_assert(!kMix || (kBN == 256 && !kLora), "mixed tiles live in the 256-wide kernel");
+  static_assert(kEG == 1 || (kEG == 2 && kBN == 256), "two epilogue groups split a 256-wide tile");
   // TMEM: kLora/128: 2 stages x (128 base + 128 L); kLora/256: ONE stage of 256 base + 256 L (the 256-wide tile
   // halves the L2 traffic per FLOP of the 128-wide one, which is what bounds these launches; the price is
   // that a tile's epilogue no longer overlaps the next mainloop); otherwise 2 stages x kBN
@@ -219,7 +221,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's barrier
+      mbar_init(&tempty_bar[s], 8 * kEG);  // every epilogue warp of both CTAs arrives on the leader's barrier
       mbar_init(&res_bar[s], 1);
     }
     fence_barrier_init();
@@ -243,8 +245,8 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       const Tile2 tc = decode2(p, t);
       const Gemm2Group& G = p.g[tc.g];
       const int my_m = tc.m0 + rank * kRows;
-      const int bnt = kMix ? G.bn : kBN;                         // this tile's width
-      const bool lora_tile = kLora || (kMix && G.lora != 0);
+      constexpr int bnt = kBN;
+      constexpr bool lora_tile = kLora;
       const uint32_t stage_tx = 2u * (kStageA + (bnt / 2) * kBK * 2);  // both CTAs: A rows + their half of W
       const int my_n = tc.n0 + rank * (bnt / 2);
       PixTile pt{0, 0};
@@ -301,10 +303,9 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kBN;
       long long stall = 0;
-      const Gemm2Group& GM = p.g[decode2(p, t).g];
-      const bool lora_tile = kLora || (kMix && GM.lora != 0);
-      const uint32_t idesc_t = kMix ? make_idesc_bf16(256, static_cast<uint32_t>(GM.bn), 0, 0) : idesc;
-      const uint32_t l_off = kMix ? 128u : kLoraOff;  // column offset of the low-rank accumulator
+      constexpr bool lora_tile = kLora;
+      constexpr uint32_t idesc_t = idesc;
+      constexpr uint32_t l_off = kLoraOff;  // column offset of the low-rank accumulator
       if (lora_tile) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -342,26 +343,34 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs) =====================
     const int ew = warp & 3;
+    const int eg = (kEG == 2) ? ((warp - 4) >> 2) : 0;  // epilogue group: columns [128 eg, 128 eg + 128) when kEG == 2
     const int r_in = ew * 32 + lane;          // row inside this CTA's 128 rows == TMEM lane
-    const bool issuer = (warp == 4 && lane == 0);
+    const bool issuer = (ew == 0 && lane == 0);  // one per group
+    const uint32_t bar_id = 1 + eg;
     const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
     int as = 0;
     uint32_t aphase = 0;
-    uint32_t cc = 0;  // running 64-column chunk counter (selects out_box / res_box and parities)
+    // running 64-column chunk counter of this group.  kEG == 1: two staging / residual boxes alternate by
+    // cc & 1; kEG == 2: each group has ONE of each (box index eg), the other group is what overlaps the waits.
+    uint32_t cc = 0;
+    const int c_first = (kEG == 2) ? 2 * eg : 0;
 
-    if constexpr (EPI == EPI_GATE_RES) {
-      if (issuer && pair < p.total_tiles) {  // residual of the first chunk of the first tile
-        const Tile2 tc = decode2(p, pair);
-        mbar_arrive_expect_tx(&res_bar[0], kBox);
-        if (p.g[tc.g].conv_w != 0) {
-          const PixTile q = pix_tile(p.g[tc.g], tc.m0 + rank * kRows);
-          tma_load_3d(res_box, &p.g[tc.g].tmRes, &res_bar[0], tc.n0, q.x0 + 1, q.y0 + 1);
-        } else {
-          tma_load_2d(res_box, &p.g[tc.g].tmRes, &res_bar[0], tc.n0, tc.m0 + rank * kRows);
-        }
+    // residual prefetch of chunk `nc` of tile `nt` into box `nb` (EPI_GATE_RES)
+    auto prefetch_res = [&](int nt, int nc, uint32_t nb) {
+      if (nt >= p.total_tiles) return;
+      const Tile2 tn = decode2(p, nt);
+      mbar_arrive_expect_tx(&res_bar[nb], kBox);
+      if (p.g[tn.g].conv_w != 0) {
+        const PixTile q = pix_tile(p.g[tn.g], tn.m0 + rank * kRows);
+        tma_load_3d(res_box + nb * kBox, &p.g[tn.g].tmRes, &res_bar[nb], tn.n0 + nc * 64, q.x0 + 1, q.y0 + 1);
+      } else {
+        tma_load_2d(res_box + nb * kBox, &p.g[tn.g].tmRes, &res_bar[nb], tn.n0 + nc * 64, tn.m0 + rank * kRows);
       }
+    };
+    if constexpr (EPI == EPI_GATE_RES) {
+      if (issuer) prefetch_res(pair, c_first, kEG == 2 ? eg : 0);  // first chunk of the first tile
     }
-    const bool etr = p.trace != nullptr && pair == 0 && leader && issuer;
+    const bool etr = p.trace != nullptr && pair == 0 && leader && issuer && eg == 0;
     int eti = 0;
     for (int t = pair; t < p.total_tiles; t += npairs, ++eti) {
       const Tile2 tc = decode2(p, t);
@@ -374,13 +383,11 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
       if (etr && eti < 16) p.trace[eti * 8 + 4] = clock64();
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_off + as * kBN;
-      const int bnt = kMix ? G.bn : kBN;
-      const bool lora_tile = kLora || (kMix && G.lora != 0);
-      const uint32_t l_off = kMix ? 128u : kLoraOff;
+      constexpr int bnt = kBN;
+      constexpr uint32_t l_off = kLoraOff;
       // v = bf16(v + bf16(L)): the low-rank term of this 64-column chunk from its own accumulator
       auto lora_add = [&](uint32_t col, float (&v)[64]) {
-        if constexpr (kLora || kMix) {
-          if (!lora_tile) return;
+        if constexpr (kLora) {
           uint32_t accl[64];
           tmem_ld64(taddr + l_off + col, accl);
 #pragma unroll
@@ -394,14 +401,20 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         }
       };
 
-      // issue the box store of chunk `cc` (all 128 epilogue threads call this)
-      auto publish = [&](const float (&v)[64], int col) {
-        uint8_t* ob = out_box + (cc & 1) * kBox;
-        if (issuer) tma_store_wait_read<1>();  // the store that last used this box has drained
-        named_bar_sync(1, 128);
+      // issue the box store of chunk `cc` (all 128 threads of the group call this); `nt`/`nc`: the group's next
+      // chunk, whose residual (kEG == 2) is fetched into the single residual box once everybody has read it
+      auto publish = [&](const float (&v)[64], int col, int nt, int nc) {
+        uint8_t* ob = out_box + (kEG == 2 ? eg : (cc & 1)) * kBox;
+        if (issuer) {  // the store that last used this box has drained
+          if constexpr (kEG == 2) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+        }
+        named_bar_sync(bar_id, 128);
+        if constexpr (EPI == EPI_GATE_RES && kEG == 2) {
+          if (issuer) prefetch_res(nt, nc, eg);
+        }
         box_store_row(ob, r_in, v);
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
         if (issuer) {
           if (G.conv_w != 0) {
             const PixTile q = pix_tile(G, my_m);
@@ -419,7 +432,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
         const float* cosr = G.rope_cos + static_cast<size_t>(row_c) * 64;
         const float* sinr = G.rope_sin + static_cast<size_t>(row_c) * 64;
 #pragma unroll 1
-        for (int hc = 0; hc < bnt / 128; ++hc) {
+        for (int hc = (kEG == 2 ? eg : 0); hc < (kEG == 2 ? eg + 1 : bnt / 128); ++hc) {
           const int col_h = tc.n0 + hc * 128;
           const int section = col_h / inner;  // 0 q, 1 k, 2 v
           const bf16* bias_h = G.bias ? G.bias + col_h : nullptr;
@@ -480,37 +493,29 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
               linear_round64(acc, bias_h ? bias_h + c * 64 : nullptr, add_h ? add_h + c * 64 : nullptr, v);
               lora_add(hc * 128 + c * 64, v);
             }
-            publish(v, col_h + c * 64);
+            publish(v, col_h + c * 64, 0, 0);
             ++cc;
           }
         }
       } else {
         const bf16* add_r = G.addend ? G.addend + static_cast<size_t>(row_c) * G.ldadd + tc.n0 : nullptr;
+        const int c_end = (kEG == 2) ? c_first + 2 : bnt / 64;
 #pragma unroll 1
-        for (int c = 0; c < bnt / 64; ++c) {
+        for (int c = c_first; c < c_end; ++c) {
           float r[64];
+          int nt = t, nc = c + 1;  // this group's next chunk
+          if (nc == c_end) { nt = t + npairs; nc = c_first; }
           if constexpr (EPI == EPI_GATE_RES) {
-            // prefetch the residual of the NEXT chunk into the other box (everybody finished reading
-            // it before the barriers inside publish() of the previous chunk)
-            if (issuer) {
-              int nt = t, nc = c + 1;
-              if (nc == bnt / 64) { nt = t + npairs; nc = 0; }
-              if (nt < p.total_tiles) {
-                const Tile2 tn = decode2(p, nt);
-                const uint32_t nb = (cc + 1) & 1;
-                mbar_arrive_expect_tx(&res_bar[nb], kBox);
-                if (p.g[tn.g].conv_w != 0) {
-                  const PixTile q = pix_tile(p.g[tn.g], tn.m0 + rank * kRows);
-                  tma_load_3d(res_box + nb * kBox, &p.g[tn.g].tmRes, &res_bar[nb], tn.n0 + nc * 64,
-                              q.x0 + 1, q.y0 + 1);
-                } else {
-                  tma_load_2d(res_box + nb * kBox, &p.g[tn.g].tmRes, &res_bar[nb], tn.n0 + nc * 64,
-                              tn.m0 + rank * kRows);
-                }
-              }
+            if constexpr (kEG == 1) {
+              // prefetch the residual of the NEXT chunk into the other box (everybody finished reading
+              // it before the barriers inside publish() of the previous chunk)
+              if (issuer) prefetch_res(nt, nc, (cc + 1) & 1);
+              mbar_wait(&res_bar[cc & 1], (cc >> 1) & 1);
+              box_load_row(res_box + (cc & 1) * kBox, r_in, r);
+            } else {
+              mbar_wait(&res_bar[eg], cc & 1);
+              box_load_row(res_box + eg * kBox, r_in, r);
             }
-            mbar_wait(&res_bar[cc & 1], (cc >> 1) & 1);
-            box_load_row(res_box + (cc & 1) * kBox, r_in, r);
           }
           uint32_t acc[64];
           tmem_ld64(taddr + c * 64, acc);
@@ -540,7 +545,7 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
               }
             }
           }
-          publish(v, tc.n0 + c * 64);
+          publish(v, tc.n0 + c * 64, nt, nc);
           ++cc;
         }
       }
@@ -563,11 +568,11 @@ gemm2_kernel(const __grid_constant__ Gemm2Params p) {
 }
 
 // ------------------------------------------------------------------------------------ host
-template <int EPI, int BN, bool LORA = false, bool MIX = false>
+template <int EPI, int BN, bool LORA = false, int EG = 1>
 static int set_attr2() {
   static bool done = false;
   if (!done) {
-    RF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI, BN, LORA, MIX>,
+    RF_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI, BN, LORA, EG>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmem));
     done = true;
   }
@@ -578,14 +583,22 @@ int gemm2_init() {
           set_attr2<EPI_QKV, 256>() | set_attr2<EPI_BIAS, 128>() | set_attr2<EPI_GATE_RES, 128>() |
           set_attr2<EPI_GELU, 128, true>() | set_attr2<EPI_GATE_RES, 128, true>() |
           set_attr2<EPI_QKV, 128, true>() | set_attr2<EPI_GELU, 256, true>() | set_attr2<EPI_GATE_RES, 256, true>() |
-          set_attr2<EPI_QKV, 256, true>() | set_attr2<EPI_GELU, 256, false, true>() |
-          set_attr2<EPI_GATE_RES, 256, false, true>() | set_attr2<EPI_QKV, 256, false, true>())
+          set_attr2<EPI_QKV, 256, true>() | set_attr2<EPI_BIAS, 256, false, 2>() |
+          set_attr2<EPI_GELU, 256, false, 2>() | set_attr2<EPI_GATE_RES, 256, false, 2>() |
+          set_attr2<EPI_QKV, 256, false, 2>() | set_attr2<EPI_GELU, 256, true, 2>() |
+          set_attr2<EPI_GATE_RES, 256, true, 2>() | set_attr2<EPI_QKV, 256, true, 2>())
              ? -2
              : 0;
 }
 
 long long* dbg_get_gemm_trace();
-template <int EPI, int BN, bool LORA = false, bool MIX = false>
+// RF_GEMM_EPI_GROUPS = 1 | 2 (read per launch, i.e. at graph-capture time): epilogue warpgroups of the 256-wide
+// kernels.  Default 2.
+static int epi_groups() {
+  const char* e = getenv("RF_GEMM_EPI_GROUPS");
+  return (e && e[0] == '1') ? 1 : 2;
+}
+template <int EPI, int BN, bool LORA = false, int EG = 1>
 static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t stream) {
   Gemm2Params p = p_in;
   p.trace = dbg_get_gemm_trace();
@@ -595,14 +608,14 @@ static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t
     p.dbg_skip = skip;
   }
 #endif
-  if (int rc = set_attr2<EPI, BN, LORA, MIX>()) return rc;
+  if (int rc = set_attr2<EPI, BN, LORA, EG>()) return rc;
   static const char* kNames[4] = {"gemm_bias", "gemm_gelu", "gemm_gate_res", "gemm_qkv_rms_rope"};
   const char* name = p.g[0].conv_w ? (EPI == EPI_GATE_RES ? "conv_res" : "conv_bias") : kNames[EPI];
   ProfScope prof(name, 2.0 * rows * p.N * p.K,
                  2.0 * (rows * p.K / (p.g[0].conv_w ? p.g[0].conv_taps : 1) +
                         static_cast<double>(p.ngroups) * p.N * p.K + rows * p.N),
                  stream);
-  RF_CHECK_CUDA(launch_pdl(gemm2_kernel<EPI, BN, LORA, MIX>, dim3(2 * pairs), dim3(kThreads2), Cfg2<BN>::kSmem, stream, p));
+  RF_CHECK_CUDA(launch_pdl(gemm2_kernel<EPI, BN, LORA, EG>, dim3(2 * pairs), dim3(kThreads2 + 128 * (EG - 1)), Cfg2<BN>::kSmem, stream, p));
   count_launch();
   return 0;
 }
@@ -632,6 +645,15 @@ static int gemm2_dispatch(int epi, Gemm2Params& p, int tiles, double rows, cudaS
     if (epi == EPI_GATE_RES) return launch2<EPI_GATE_RES, 128>(p, pairs, rows, stream);
     set_error("gemm2: 128-wide tiles support the bias and residual epilogues only");
     return -1;
+  }
+  if (epi_groups() == 2) {
+    switch (epi) {
+      case EPI_BIAS: return launch2<EPI_BIAS, 256, false, 2>(p, pairs, rows, stream);
+      case EPI_GELU: return launch2<EPI_GELU, 256, false, 2>(p, pairs, rows, stream);
+      case EPI_GATE_RES: return launch2<EPI_GATE_RES, 256, false, 2>(p, pairs, rows, stream);
+      case EPI_QKV: return launch2<EPI_QKV, 256, false, 2>(p, pairs, rows, stream);
+      default: break;
+    }
   }
   switch (epi) {
     case EPI_BIAS: return launch2<EPI_BIAS, 256>(p, pairs, rows, stream);
@@ -701,84 +723,6 @@ int gemm2_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups
   return gemm2_dispatch(epi, p, tiles, rows, stream);
 }
 
-// Grouped launch whose LAST group (the condition stream) carries a fused peft LoRA: its tiles are 256 x 128
-// with the low-rank accumulator in the second half of the accumulator stage; the other groups keep the
-// 256 x 256 tiles.  T / loraB / sec_cols as in gemm2_lora_launch.
-bool gemm2_mixed_eligible(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups) {
-  if (ngroups < 2 || !gemm2_eligible(epi, N, K, ngroups, groups)) return false;
-  return gemm2_lora_eligible(epi, N, K, groups[ngroups - 1]);
-}
-int gemm2_mixed_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups, const bf16* T, int ldT,
-                       const bf16* loraB, int sec_cols, cudaStream_t stream) {
-  Gemm2Params p;
-  memset(&p, 0, sizeof(p));
-  p.ngroups = ngroups;
-  p.N = N;
-  p.K = K;
-  p.bn = 256;
-  p.n_tiles = N / 256;
-  p.num_kb = K / kBK;
-  p.band = p.n_tiles <= 12 ? p.n_tiles : 4;
-  int tiles = 0;
-  double rows = 0;
-  for (int g = 0; g < ngroups; ++g) {
-    const GemmGroupArgs& a = groups[g];
-    Gemm2Group& d = p.g[g];
-    const bool lora = g == ngroups - 1;
-    d.bn = lora ? 128 : 256;
-    d.n_tiles = N / d.bn;
-    d.band = lora ? (d.n_tiles <= 24 ? d.n_tiles : 8) : p.band;
-    d.lora = lora ? 1 : 0;
-    int rc = make_tmap_2d(&d.tmA, a.A, a.M, K, a.lda, kRows);
-    if (rc) return rc;
-    rc = make_tmap_2d(&d.tmB, a.W, N, K, K, d.bn / 2);
-    if (rc) return rc;
-    rc = make_tmap_2d(&d.tmOut, a.out, a.M, N, a.ldo, kRows);
-    if (rc) return rc;
-    if (epi == EPI_GATE_RES) {
-      if (a.res == nullptr || a.gate == nullptr) {
-        set_error("gemm2_mixed_launch: EPI_GATE_RES needs res and gate");
-        return -1;
-      }
-      rc = make_tmap_2d(&d.tmRes, a.res, a.M, N, a.ldr, kRows);
-      if (rc) return rc;
-    }
-    if (epi == EPI_QKV && (!a.rope_cos || !a.rope_sin || !a.norm_q || !a.norm_k)) {
-      set_error("gemm2_mixed_launch: EPI_QKV needs rope tables and norm weights");
-      return -1;
-    }
-    if (lora) {
-      const int t_cols = sec_cols > 0 ? (N / sec_cols) * 64 : 64;
-      rc = make_tmap_2d(&d.tmT, T, a.M, t_cols, ldT, kRows);
-      if (rc) return rc;
-      rc = make_tmap_2d(&d.tmLB, loraB, N, 64, 64, d.bn / 2);
-      if (rc) return rc;
-      d.lora_sec_cols = sec_cols;
-    }
-    d.bias = a.bias; d.addend = lora ? nullptr : a.addend; d.gate = a.gate;
-    d.rope_cos = a.rope_cos; d.rope_sin = a.rope_sin; d.norm_q = a.norm_q; d.norm_k = a.norm_k;
-    d.M = a.M; d.ldadd = a.ldadd;
-    d.m_pairs = (a.M + 2 * kRows - 1) / (2 * kRows);
-    d.tile_begin = tiles;
-    tiles += d.m_pairs * d.n_tiles;
-    rows += a.M;
-  }
-  p.total_tiles = tiles;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int pairs = sms / 2;
-  if (pairs > tiles) pairs = tiles;
-  switch (epi) {
-    case EPI_GELU: return launch2<EPI_GELU, 256, false, true>(p, pairs, rows, stream);
-    case EPI_GATE_RES: return launch2<EPI_GATE_RES, 256, false, true>(p, pairs, rows, stream);
-    case EPI_QKV: return launch2<EPI_QKV, 256, false, true>(p, pairs, rows, stream);
-    default: break;
-  }
-  set_error("gemm2_mixed_launch: unsupported epilogue");
-  return -1;
-}
-
 // One token stream (the condition tokens) with peft LoRA fused: out = epi(bf16(bf16(A W^T + b) + bf16(T B^T))),
 // T = bf16(A lora_A^T) computed beforehand ([M, ldT]; columns [64 s, 64 s + 64) belong to output section
 // s = n / sec_cols when sec_cols > 0 — the stacked q|k|v projection), lora_B [N, 64] (rank zero-padded to 64).
@@ -842,7 +786,14 @@ int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16*
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;
-  if (p.bn == 256) {
+  if (p.bn == 256 && epi_groups() == 2) {
+    switch (epi) {
+      case EPI_GELU: return launch2<EPI_GELU, 256, true, 2>(p, pairs, a.M, stream);
+      case EPI_GATE_RES: return launch2<EPI_GATE_RES, 256, true, 2>(p, pairs, a.M, stream);
+      case EPI_QKV: return launch2<EPI_QKV, 256, true, 2>(p, pairs, a.M, stream);
+      default: break;
+    }
+  } else if (p.bn == 256) {
     switch (epi) {
       case EPI_GELU: return launch2<EPI_GELU, 256, true>(p, pairs, a.M, stream);
       case EPI_GATE_RES: return launch2<EPI_GATE_RES, 256, true>(p, pairs, a.M, stream);

@@ -101,12 +101,6 @@ bool gemm2_lora_eligible(int epi, int N, int K, const GemmGroupArgs& a);
 int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16* T, int ldT,
                       const bf16* loraB, int sec_cols, cudaStream_t stream);
 
-// grouped launch whose LAST group carries the fused LoRA (256 x 128 tiles with the low-rank accumulator in the
-// second half of the accumulator stage) while the other groups run the usual 256 x 256 tiles
-bool gemm2_mixed_eligible(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups);
-int gemm2_mixed_launch(int epi, int N, int K, int ngroups, const GemmGroupArgs* groups, const bf16* T, int ldT,
-                       const bf16* loraB, int sec_cols, cudaStream_t stream);
-
 // LoRA down-projection of one token stream: T[M, NT] = bf16(X[M, K] @ A[NT, K]^T), NT = 64 | 192 | 256,
 // split-K over the SMs with a deterministic in-kernel reduction (lora_down_sm100.cu).  `ws` holds
 // lora_down_workspace_bytes(M, NT) bytes and must be zeroed once before its first use.
