@@ -175,10 +175,10 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
                make_smem_desc(k + off, 16, 1024, 2), idesc_qk, kk != 0 ? 1u : 0u);
       }
     };
-    auto issue_pv = [&](int t, int st, bool acc, int k0) {  // k-steps [k0, k0 + 4)
+    auto issue_pv = [&](int t, int st, bool acc, int k0, int k1) {  // k-steps [k0, k1)
       const uint32_t v = aV + st * kTileBytes;
 #pragma unroll
-      for (int kk = k0; kk < k0 + 4; ++kk) {
+      for (int kk = k0; kk < k1; ++kk) {
         // 16 kv rows per step: P columns advance by 8 (16 bf16), V by 16 rows x 128 B
         mma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8,
                make_smem_desc(v + kk * 2048, kHalfBytes, 1024, 2), idesc_pv,
@@ -207,13 +207,13 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
       mbar_wait(&p_lo[0], pj);
       RF_TR(0, j);
       tc_fence_after();
-      if (elect_one()) issue_pv(0, st, j != 0, 0);  // first half of P_A: overlaps the rest of A's softmax
+      if (elect_one()) issue_pv(0, st, j != 0, 0, 6);  // p_lo arrives once the stores of P chunks 0..2 have landed: 6 of the 8 k-steps run under the last chunk's exponentials
       __syncwarp();
       mbar_wait(&p_hi[0], pj);
       if (more) mbar_wait(&k_full[st2], ph2);
       tc_fence_after();
       if (elect_one()) {
-        issue_pv(0, st, true, 4);
+        issue_pv(0, st, true, 6, 8);
         if (more) {
           issue_qk(0, st2);
           tc_commit(&s_full[0]);
@@ -224,12 +224,12 @@ attn_kernel(const __grid_constant__ AttnParamsDev p) {
       mbar_wait(&p_lo[1], pj);
       RF_TR(2, j);
       tc_fence_after();
-      if (elect_one()) issue_pv(1, st, j != 0, 0);
+      if (elect_one()) issue_pv(1, st, j != 0, 0, 6);
       __syncwarp();
       mbar_wait(&p_hi[1], pj);
       tc_fence_after();
       if (elect_one()) {
-        issue_pv(1, st, true, 4);
+        issue_pv(1, st, true, 6, 8);
         tc_commit(&v_empty[st]);
         if (more) {
           issue_qk(1, st2);
