@@ -592,11 +592,16 @@ int gemm2_init() {
 }
 
 long long* dbg_get_gemm_trace();
-// RF_GEMM_EPI_GROUPS = 1 | 2 (read per launch, i.e. at graph-capture time): epilogue warpgroups of the 256-wide
-// kernels.  Default 2.
-static int epi_groups() {
-  const char* e = getenv("RF_GEMM_EPI_GROUPS");
-  return (e && e[0] == '1') ? 1 : 2;
+// Epilogue warpgroups of the 256-wide kernels (read per launch, i.e. at graph-capture time).
+//   RF_GEMM_EPI_GROUPS (default 1): the double-buffered kernels.  Measured (tools/trace_gemm.py, step_ab.py): their
+//     epilogues (6-11 k cycles; QKV 25 k) already hide under the 30 k-cycle mainloop of even the K = 3072 tiles, and
+//     two groups only add register spills and issue pressure: entry A 64.3 vs 63.3 ms.
+//   RF_LORA_EPI_GROUPS (default 2): the single-accumulator-stage LoRA kernels, whose epilogue is NOT overlapped.
+static int epi_groups(bool lora) {
+  const char* e = getenv(lora ? "RF_LORA_EPI_GROUPS" : "RF_GEMM_EPI_GROUPS");
+  const int dflt = lora ? 2 : 1;
+  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  return dflt;
 }
 template <int EPI, int BN, bool LORA = false, int EG = 1>
 static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t stream) {
@@ -646,7 +651,7 @@ static int gemm2_dispatch(int epi, Gemm2Params& p, int tiles, double rows, cudaS
     set_error("gemm2: 128-wide tiles support the bias and residual epilogues only");
     return -1;
   }
-  if (epi_groups() == 2) {
+  if (epi_groups(false) == 2) {
     switch (epi) {
       case EPI_BIAS: return launch2<EPI_BIAS, 256, false, 2>(p, pairs, rows, stream);
       case EPI_GELU: return launch2<EPI_GELU, 256, false, 2>(p, pairs, rows, stream);
@@ -786,7 +791,7 @@ int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16*
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;
-  if (p.bn == 256 && epi_groups() == 2) {
+  if (p.bn == 256 && epi_groups(true) == 2) {
     switch (epi) {
       case EPI_GELU: return launch2<EPI_GELU, 256, true, 2>(p, pairs, a.M, stream);
       case EPI_GATE_RES: return launch2<EPI_GATE_RES, 256, true, 2>(p, pairs, a.M, stream);
