@@ -28,6 +28,7 @@ struct alignas(64) LoraDownParams {
   unsigned* done;
   bf16* T;
   int ldT, M, num_kb, splits, kb_per, m_tiles;
+  int n_blocks;  // > 1: full-K CTAs per 64-column block of T (no split-K, no workspace): NT == 64, splits == 1
 };
 
 template <int NT>
@@ -52,8 +53,10 @@ __global__ void __launch_bounds__(kLdThreads, 1) lora_down_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mt = blockIdx.x / p.splits;
-  const int sp = blockIdx.x - mt * p.splits;
+  const int tile = blockIdx.x / p.splits;
+  const int sp = blockIdx.x - tile * p.splits;
+  const int mt = tile / p.n_blocks;
+  const int nb = tile - mt * p.n_blocks;
   const int kb0 = sp * p.kb_per;
   const int kb1 = min(p.num_kb, kb0 + p.kb_per);
   const int nkb = kb1 - kb0;  // >= 1 by construction of the launch
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(kLdThreads, 1) lora_down_kernel(const __grid_c
       uint8_t* sa = smem + stage * kStage;
       mbar_arrive_expect_tx(&full_bar[stage], kStage);
       tma_load_2d(sa, &p.tmX, &full_bar[stage], kb * 64, mt * 128);
-      tma_load_2d(sa + LdCfg<NT>::kStageA, &p.tmA, &full_bar[stage], kb * 64, 0);
+      tma_load_2d(sa + LdCfg<NT>::kStageA, &p.tmA, &full_bar[stage], kb * 64, nb * NT);
       if (++stage == kLdStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
@@ -117,6 +120,27 @@ __global__ void __launch_bounds__(kLdThreads, 1) lora_down_kernel(const __grid_c
     float* wrow = p.ws + (static_cast<size_t>(sp) * rows_pad + row) * NT;
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
+    if (p.splits == 1) {  // the whole K ran in this CTA: round and store the bf16 rows directly
+      if (row < p.M) {
+        bf16* trow = p.T + static_cast<size_t>(row) * p.ldT + nb * NT;
+#pragma unroll 1
+        for (int c = 0; c < NT / 32; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + c * 32, acc);
+          tmem_ld_wait();
+          uint4* dst = reinterpret_cast<uint4*>(trow + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(acc[8 * q]), __uint_as_float(acc[8 * q + 1]));
+            o.y = pack_bf16x2(__uint_as_float(acc[8 * q + 2]), __uint_as_float(acc[8 * q + 3]));
+            o.z = pack_bf16x2(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5]));
+            o.w = pack_bf16x2(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7]));
+            dst[q] = o;
+          }
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int c = 0; c < NT / 32; ++c) {
       uint32_t acc[32];
@@ -186,6 +210,7 @@ __global__ void __launch_bounds__(kLdThreads, 1) lora_down_kernel(const __grid_c
         p.done[mt] = 0u;
       }
     }
+    }  // splits > 1
   }
 
   tc_fence_before();
@@ -232,6 +257,27 @@ int lora_down_launch(const bf16* X, int ldx, int M, int K, const bf16* A, int NT
   if (rc) return rc;
   p.m_tiles = (M + 127) / 128;
   p.num_kb = K / 64;
+  p.n_blocks = 1;
+  // short K, wide T (the stacked q|k|v[|mlp] factors, K = 3072): one full-K CTA per (128 rows, 64 columns) —
+  // x is re-read NT/64 times from L2 but nothing goes through the split-K workspace (the partial store, the
+  // arrival wait and the L2 round trips of the reduction were ~2/3 of the 19 us such a launch took)
+  if (NT >= 128 && p.num_kb <= 64) {
+    int rc2 = make_tmap_2d(&p.tmA, A, NT, K, K, 64);
+    if (rc2) return rc2;
+    p.n_blocks = NT / 64;
+    p.splits = 1;
+    p.kb_per = p.num_kb;
+    p.ws = nullptr;
+    p.counters = p.done = nullptr;
+    p.T = T;
+    p.ldT = ldT;
+    p.M = M;
+    ProfScope prof("lora_down", 2.0 * M * NT * static_cast<double>(K), 2.0 * (static_cast<double>(M) * K + static_cast<double>(NT) * K), stream);
+    if ((rc2 = ld_set_attr<64>())) return rc2;
+    RF_CHECK_CUDA(launch_pdl(lora_down_kernel<64>, dim3(p.m_tiles * p.n_blocks), dim3(kLdThreads), LdCfg<64>::kSmem, stream, p));
+    count_launch();
+    return 0;
+  }
   // >= 6 k-blocks per CTA, at most kLdMaxSplits splits, and no more CTAs than fit one wave
   int splits = p.num_kb / 6;
   if (splits < 1) splits = 1;
