@@ -583,26 +583,24 @@ int gemm2_init() {
           set_attr2<EPI_QKV, 256>() | set_attr2<EPI_BIAS, 128>() | set_attr2<EPI_GATE_RES, 128>() |
           set_attr2<EPI_GELU, 128, true>() | set_attr2<EPI_GATE_RES, 128, true>() |
           set_attr2<EPI_QKV, 128, true>() | set_attr2<EPI_GELU, 256, true>() | set_attr2<EPI_GATE_RES, 256, true>() |
-          set_attr2<EPI_QKV, 256, true>() | set_attr2<EPI_BIAS, 256, false, 2>() |
-          set_attr2<EPI_GELU, 256, false, 2>() | set_attr2<EPI_GATE_RES, 256, false, 2>() |
-          set_attr2<EPI_QKV, 256, false, 2>() | set_attr2<EPI_GELU, 256, true, 2>() |
-          set_attr2<EPI_GATE_RES, 256, true, 2>() | set_attr2<EPI_QKV, 256, true, 2>())
+          set_attr2<EPI_QKV, 256, true>())
              ? -2
              : 0;
 }
 
 long long* dbg_get_gemm_trace();
-// Epilogue warpgroups of the 256-wide kernels (read per launch, i.e. at graph-capture time).
-//   RF_GEMM_EPI_GROUPS (default 1): the double-buffered kernels.  Measured (tools/trace_gemm.py, step_ab.py): their
-//     epilogues (6-11 k cycles; QKV 25 k) already hide under the 30 k-cycle mainloop of even the K = 3072 tiles, and
-//     two groups only add register spills and issue pressure: entry A 64.3 vs 63.3 ms.
-//   RF_LORA_EPI_GROUPS (default 2): the single-accumulator-stage LoRA kernels, whose epilogue is NOT overlapped.
+// Epilogue warpgroups of the 256-wide kernels.  The two-group form (kEG = 2) is a measured dead end and is only
+// instantiated in DEV builds (make DEV=1; RF_GEMM_EPI_GROUPS=2 / RF_LORA_EPI_GROUPS=2, read at graph-capture time):
+// the epilogues of the double-buffered kernels (6-11 k cycles; QKV 25 k — tools/trace_gemm.py) already hide under
+// the 30 k-cycle mainloop of even the K = 3072 tiles, and a second group only adds register spills and issue
+// pressure — entry A 64.3 vs 63.3 ms, entry B 91.5 vs 89.6 ms; on the single-stage LoRA kernels alone: no gain
+// either (tools/step_ab.py, profiles/r02_ab_runs.md).
+#ifdef RF_DEV_HOOKS
 static int epi_groups(bool lora) {
   const char* e = getenv(lora ? "RF_LORA_EPI_GROUPS" : "RF_GEMM_EPI_GROUPS");
-  const int dflt = lora ? 2 : 1;
-  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
-  return dflt;
+  return (e && e[0] == '2') ? 2 : 1;
 }
+#endif
 template <int EPI, int BN, bool LORA = false, int EG = 1>
 static int launch2(const Gemm2Params& p_in, int pairs, double rows, cudaStream_t stream) {
   Gemm2Params p = p_in;
@@ -651,6 +649,7 @@ static int gemm2_dispatch(int epi, Gemm2Params& p, int tiles, double rows, cudaS
     set_error("gemm2: 128-wide tiles support the bias and residual epilogues only");
     return -1;
   }
+#ifdef RF_DEV_HOOKS
   if (epi_groups(false) == 2) {
     switch (epi) {
       case EPI_BIAS: return launch2<EPI_BIAS, 256, false, 2>(p, pairs, rows, stream);
@@ -660,6 +659,7 @@ static int gemm2_dispatch(int epi, Gemm2Params& p, int tiles, double rows, cudaS
       default: break;
     }
   }
+#endif
   switch (epi) {
     case EPI_BIAS: return launch2<EPI_BIAS, 256>(p, pairs, rows, stream);
     case EPI_GELU: return launch2<EPI_GELU, 256>(p, pairs, rows, stream);
@@ -791,6 +791,7 @@ int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16*
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;
+#ifdef RF_DEV_HOOKS
   if (p.bn == 256 && epi_groups(true) == 2) {
     switch (epi) {
       case EPI_GELU: return launch2<EPI_GELU, 256, true, 2>(p, pairs, a.M, stream);
@@ -798,7 +799,9 @@ int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16*
       case EPI_QKV: return launch2<EPI_QKV, 256, true, 2>(p, pairs, a.M, stream);
       default: break;
     }
-  } else if (p.bn == 256) {
+  }
+#endif
+  if (p.bn == 256) {
     switch (epi) {
       case EPI_GELU: return launch2<EPI_GELU, 256, true>(p, pairs, a.M, stream);
       case EPI_GATE_RES: return launch2<EPI_GATE_RES, 256, true>(p, pairs, a.M, stream);
