@@ -18,7 +18,7 @@
 namespace rf {
 
 static constexpr int kLdThreads = 256;
-static constexpr int kLdStages = 4;
+template <int NT> struct LdStages { static constexpr int v = (NT <= 64) ? 8 : 4; };  // 24 KB stages: 8 deep covers the L2 / HBM latency of a lone CTA stream
 static constexpr int kLdMaxSplits = 16;
 
 struct alignas(64) LoraDownParams {
@@ -37,12 +37,14 @@ struct LdCfg {
   static constexpr int kStageB = NT * 64 * 2;
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kTmemCols = NT <= 64 ? 64 : 256;
-  static constexpr int kSmem = kLdStages * kStage + 1024 + 256;
+  static constexpr int kStages = LdStages<NT>::v;
+  static constexpr int kSmem = kStages * kStage + 1024 + 256;
 };
 
 template <int NT>
 __global__ void __launch_bounds__(kLdThreads, 1) lora_down_kernel(const __grid_constant__ LoraDownParams p) {
   constexpr int kStage = LdCfg<NT>::kStage;
+  constexpr int kLdStages = LdCfg<NT>::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
