@@ -636,13 +636,30 @@ bool gemm2_eligible(int epi, int N, int K, int ngroups, const GemmGroupArgs* gro
   return true;
 }
 
+static thread_local int g_reserve_pairs = 0;
+int gemm2_reserve_pairs(int pairs) {
+  const int prev = g_reserve_pairs;
+  g_reserve_pairs = pairs < 0 ? 0 : pairs;
+  return prev;
+}
+// persistent grid: one CTA pair per TPC, minus the reserved ones when the tiles still take the same number of waves
+static int gemm2_grid_pairs(int tiles) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  int pairs = sms / 2;
+  const int fewer = pairs - g_reserve_pairs;
+  if (g_reserve_pairs > 0 && fewer > 0 && (tiles + fewer - 1) / fewer == (tiles + pairs - 1) / pairs) pairs = fewer;
+  if (pairs > tiles) pairs = tiles;
+  return pairs;
+}
+
 static int gemm2_dispatch(int epi, Gemm2Params& p, int tiles, double rows, cudaStream_t stream) {
   p.total_tiles = tiles;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int pairs = sms / 2;
-  if (pairs > tiles) pairs = tiles;
+  const int pairs = gemm2_grid_pairs(tiles);
   if (p.bn == 128) {
     if (epi == EPI_BIAS) return launch2<EPI_BIAS, 128>(p, pairs, rows, stream);
     if (epi == EPI_GATE_RES) return launch2<EPI_GATE_RES, 128>(p, pairs, rows, stream);
@@ -786,11 +803,7 @@ int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16*
   d.tile_begin = 0;
   const int tiles = d.m_pairs * p.n_tiles;
   p.total_tiles = tiles;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int pairs = sms / 2;
-  if (pairs > tiles) pairs = tiles;
+  const int pairs = gemm2_grid_pairs(tiles);
 #ifdef RF_DEV_HOOKS
   if (p.bn == 256 && epi_groups(true) == 2) {
     switch (epi) {

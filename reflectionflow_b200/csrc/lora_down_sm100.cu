@@ -223,6 +223,182 @@ __global__ void __launch_bounds__(kLdThreads, 1) lora_down_kernel(const __grid_c
   }
 }
 
+// ---- confined form: a few CTAs (2-CTA clusters, so that a cluster takes one TPC) walk every (m tile, 64-column
+// block) item with the full K each.  It is meant to run on a forked stream UNDER the other token streams' GEMM of the
+// same layer, which leaves `kLdSideClusters` TPCs free for it (gemm2_reserve_pairs): the 17-30 us a standalone
+// lora_down launch takes on an otherwise idle GPU disappear from the step.  No split-K, no workspace.
+static constexpr int kLdSideStages = 8;
+static constexpr int kLdSideStage = 128 * 64 * 2 + 64 * 64 * 2;  // 24 KB
+static constexpr int kLdSideSmem = kLdSideStages * kLdSideStage + 1024 + 256;
+__global__ void __launch_bounds__(kLdThreads, 1) lora_down_side_kernel(const __grid_constant__ LoraDownParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kLdSideStages * kLdSideStage);
+  uint64_t* empty_bar = full_bar + kLdSideStages;
+  uint64_t* tfull_bar = empty_bar + kLdSideStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int items = p.m_tiles * p.n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmA);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kLdSideStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<128>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int mt = it / p.n_blocks, nb = it - mt * p.n_blocks;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kLdSideStage;
+        mbar_arrive_expect_tx(&full_bar[stage], kLdSideStage);
+        tma_load_2d(sa, &p.tmX, &full_bar[stage], kb * 64, mt * 128);
+        tma_load_2d(sa + 128 * 64 * 2, &p.tmA, &full_bar[stage], kb * 64, nb * 64);
+        if (++stage == kLdSideStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int acc = n & 1;
+      mbar_wait(&tempty_bar[acc], ((n >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * 64;
+      for (int i = 0; i < p.num_kb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kLdSideStage);
+        const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(sa + 128 * 64 * 2, 16, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+        tc_commit(&empty_bar[stage]);
+        if (++stage == kLdSideStages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(&tfull_bar[acc]);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp & 3;
+    const int r_in = ew * 32 + lane;
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int mt = it / p.n_blocks, nb = it - mt * p.n_blocks;
+      const int acc = n & 1;
+      const int row = mt * 128 + r_in;
+      const uint32_t taddr = tmem_base + acc * 64 + (static_cast<uint32_t>(ew * 32) << 16);
+      mbar_wait(&tfull_bar[acc], (n >> 1) & 1);
+      tc_fence_after();
+      uint32_t lo[32], hi[32];
+      tmem_ld_32x32(taddr, lo);
+      tmem_ld_32x32(taddr + 32, hi);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (row < p.M) {
+        uint4* dst = reinterpret_cast<uint4*>(p.T + static_cast<size_t>(row) * p.ldT + nb * 64);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(lo[8 * q]), __uint_as_float(lo[8 * q + 1]));
+          o.y = pack_bf16x2(__uint_as_float(lo[8 * q + 2]), __uint_as_float(lo[8 * q + 3]));
+          o.z = pack_bf16x2(__uint_as_float(lo[8 * q + 4]), __uint_as_float(lo[8 * q + 5]));
+          o.w = pack_bf16x2(__uint_as_float(lo[8 * q + 6]), __uint_as_float(lo[8 * q + 7]));
+          dst[q] = o;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(hi[8 * q]), __uint_as_float(hi[8 * q + 1]));
+          o.y = pack_bf16x2(__uint_as_float(hi[8 * q + 2]), __uint_as_float(hi[8 * q + 3]));
+          o.z = pack_bf16x2(__uint_as_float(hi[8 * q + 4]), __uint_as_float(hi[8 * q + 5]));
+          o.w = pack_bf16x2(__uint_as_float(hi[8 * q + 6]), __uint_as_float(hi[8 * q + 7]));
+          dst[4 + q] = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+// T = bf16(X A^T) on `kLdSideClusters` TPCs (see the kernel comment).  Same result as lora_down_launch.
+int lora_down_side_launch(const bf16* X, int ldx, int M, int K, const bf16* A, int NT, bf16* T, int ldT,
+                          cudaStream_t stream) {
+  if (NT % 64 != 0 || NT <= 0 || K % 64 != 0 || K <= 0 || M <= 0 || (ldT * 2) % 16 != 0) {
+    set_error("lora_down_side: NT and K must be multiples of 64");
+    return -1;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    RF_CHECK_CUDA(cudaFuncSetAttribute(lora_down_side_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLdSideSmem));
+    attr_done = true;
+  }
+  LoraDownParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = make_tmap_2d(&p.tmX, X, M, K, ldx, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&p.tmA, A, NT, K, K, 64);
+  if (rc) return rc;
+  p.m_tiles = (M + 127) / 128;
+  p.num_kb = K / 64;
+  p.n_blocks = NT / 64;
+  p.splits = 1;
+  p.kb_per = p.num_kb;
+  p.T = T;
+  p.ldT = ldT;
+  p.M = M;
+  ProfScope prof("lora_down", 2.0 * M * NT * static_cast<double>(K), 2.0 * (static_cast<double>(M) * K + static_cast<double>(NT) * K), stream);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * kLdSideClusters);
+  cfg.blockDim = dim3(kLdThreads);
+  cfg.dynamicSmemBytes = kLdSideSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lora_down_side_kernel, p));
+  count_launch();
+  return 0;
+}
+
 template <int NT>
 static int ld_set_attr() {
   static bool done = false;

@@ -174,7 +174,11 @@ int rf_op_linear_lora(int epilogue, int M, int N, int K, const void* x, int ldx,
   // workspace = [split-K partials + counters | T (bf16 [rows, t_cols])]
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   bf16* T = reinterpret_cast<bf16*>(ws + ((rf::lora_down_workspace_bytes(M, 192) + 255) / 256) * 256);
-  int rc = rf::lora_down_launch(g.A, ldx, M, K, static_cast<const bf16*>(lora_A), t_cols, T, t_cols, ws, s);
+  // RF_LORA_DOWN=side: the confined few-CTA form the DiT forks under its main GEMM (here on the caller's stream)
+  const char* form = getenv("RF_LORA_DOWN");
+  int rc = (form && strcmp(form, "side") == 0)
+               ? rf::lora_down_side_launch(g.A, ldx, M, K, static_cast<const bf16*>(lora_A), t_cols, T, t_cols, s)
+               : rf::lora_down_launch(g.A, ldx, M, K, static_cast<const bf16*>(lora_A), t_cols, T, t_cols, ws, s);
   if (rc) return rc;
   return rf::gemm2_lora_launch(epilogue, N, K, g, T, t_cols, static_cast<const bf16*>(lora_B),
                                t_cols == 192 ? N / 3 : 0, s);

@@ -107,6 +107,14 @@ int gemm2_lora_launch(int epi, int N, int K, const GemmGroupArgs& a, const bf16*
 size_t lora_down_workspace_bytes(int M, int NT);
 int lora_down_launch(const bf16* X, int ldx, int M, int K, const bf16* A, int NT, bf16* T, int ldT,
                      void* ws, cudaStream_t stream);
+// The same product on kLdSideClusters TPCs only (2-CTA clusters walking full-K items), for a forked stream that
+// runs under a CTA-pair GEMM launched with gemm2_reserve_pairs(kLdSideClusters).  NT: any multiple of 64.
+static constexpr int kLdSideClusters = 2;
+int lora_down_side_launch(const bf16* X, int ldx, int M, int K, const bf16* A, int NT, bf16* T, int ldT,
+                          cudaStream_t stream);
+// The next CTA-pair GEMM launches of this thread leave `pairs` TPCs free when that does not add a wave of tiles
+// (0 = use every TPC).  Returns the previous value.
+int gemm2_reserve_pairs(int pairs);
 
 // ---------------------------------------------------------------------------- attention
 // Non-causal softmax(Q K^T / sqrt(128)) V over one joint token sequence.

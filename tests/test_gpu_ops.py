@@ -200,8 +200,16 @@ def _call_linear_lora(epi, x, W, bias, y, Ap, Bp, t_cols, res=None, gate=None, c
     torch.cuda.synchronize()
 
 
+@pytest.fixture(params=["split", "side"])
+def lora_down_form(request, monkeypatch):
+    """both forms of T = bf16(x A^T): the split-K launch and the confined few-CTA kernel that the DiT forks under its
+    main GEMM (csrc/lora_down_sm100.cu); the op reads RF_LORA_DOWN at call time"""
+    monkeypatch.setenv("RF_LORA_DOWN", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("M,N,K", [(1024, 3072, 3072), (1024, 3072, 15360), (256, 256, 256), (1000, 1024, 12288)])
-def test_linear_lora_gate_res(M, N, K):
+def test_linear_lora_gate_res(M, N, K, lora_down_form):
     """fused peft-LoRA GEMM (split-K down-projection + low-rank k-block in the main GEMM) at the
     headline condition-stream shapes: to_out / ff.net.2 / single proj_out (lora_controller.py:5-42)"""
     x = _randn(M, K, seed=70)
@@ -221,7 +229,7 @@ def test_linear_lora_gate_res(M, N, K):
     assert (y == ref).float().mean().item() > 0.98
 
 
-def test_linear_lora_gelu():
+def test_linear_lora_gelu(lora_down_form):
     M, N, K = 1024, 12288, 3072
     x = _randn(M, K, seed=80)
     W = _randn(N, K, scale=1.0 / math.sqrt(K), seed=81)
@@ -239,7 +247,7 @@ def test_linear_lora_gelu():
 
 
 @pytest.mark.parametrize("M,heads,K,only", [(1024, 24, 3072, None), (384, 2, 256, None), (1024, 2, 256, "k")])
-def test_linear_lora_qkv(M, heads, K, only):
+def test_linear_lora_qkv(M, heads, K, only, lora_down_form):
     """stacked q|k|v with per-section adapters (only="k": a k-only adapter — q and v get a zero term)"""
     D = heads * 128
     N = 3 * D
