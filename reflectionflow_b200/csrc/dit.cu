@@ -513,8 +513,8 @@ int enqueue_forward(rf_dit* h, const bf16* latents, const bf16* txt, const bf16*
     return rf::ln_modulate_launch(rowp(X, D, sr.row0), D, rowp(XN, D, sr.row0), D, sr.rows, D, scale,
                                   shift, sr.rows, 0, s);
   };
-  // RF_LORA_SIDE=0 keeps the down-projections on the main stream (A/B of the fork)
-  const char* side_s = getenv("RF_LORA_SIDE");  // read per enqueue (= per graph capture)
+  // RF_SIDE_STREAM=0 keeps the down-projections on the main stream (single-stream schedule; A/B of the fork)
+  const char* side_s = getenv("RF_SIDE_STREAM");  // read per enqueue (= per graph capture)
   const bool side_env = !(side_s && atoi(side_s) == 0);
   if (side_env && use_cond && !h->use_merged && h->any_lora && h->side_stream == nullptr) {
     RF_CHECK_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));

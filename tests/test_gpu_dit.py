@@ -225,6 +225,37 @@ def test_k_only_adapter_is_applied():
     m.close()
 
 
+@pytest.mark.parametrize("name", ["fwdB_1024", "denoiseB_1024_28", "fwdB_full_c256"])
+def test_forked_schedule_is_deterministic_and_equivalent(name, monkeypatch):
+    """The step forks work onto a second stream (csrc/dit.cu): the LoRA down-projections run on two reserved TPCs
+    under the image + text GEMM of the same layer.  The forked schedule must be bit-reproducible run to run (eager
+    forward and captured graph) and must agree with the single-stream schedule up to the one legitimate difference:
+    the confined down-projection accumulates the whole K in one CTA, the single-stream one sums split-K partials (fp32
+    summation order, then the same bf16 rounding; a 28-step loop amplifies the few 1-ulp flips of T).  Both schedules
+    must meet the error budget against the fp32 evaluation on their own.  The switch is read at enqueue / capture time."""
+    case = C.CASES[name]
+    m = _build(case)
+    _, lora = C.build_model(case)
+    outs = {}
+    for tag, side in (("single-stream", "0"), ("forked", "1"), ("forked-again", "1")):
+        monkeypatch.setenv("RF_SIDE_STREAM", side)
+        m.load_lora(lora, mode="exact")  # drops a captured graph: the next call re-captures under these switches
+        outs[tag] = _run_cuda(case)
+    a, b = outs["single-stream"].float(), outs["forked"].float()
+    assert torch.isfinite(a).all() and torch.isfinite(b).all()
+    assert torch.equal(outs["forked"], outs["forked-again"])
+    gold, _ = _golden()
+    true32 = gold[name + "/fp32"].float()
+    e_ref = (gold[name + "/bf16"].float() - true32).abs().mean()
+    d = (a - b).abs().mean()
+    print(f"[{name}] |single-stream - forked| mean {d:.3g} ; identical {(a == b).float().mean():.3f} ; "
+          f"reference bf16 error {e_ref:.3g} ; |x - fp32| single-stream {(a - true32).abs().mean():.3g} "
+          f"forked {(b - true32).abs().mean():.3g}")
+    assert d <= 0.5 * e_ref + 1e-5
+    for x in (a, b):
+        assert (x - true32).abs().mean() <= 1.25 * e_ref + 1e-3
+
+
 @pytest.mark.parametrize("name", ["fwdB_1024", "fwdB_full_c256"])
 def test_fused_lora_term_is_really_applied(name):
     """>= 128 condition tokens take the fused-LoRA GEMMs (split-K down-projection + low-rank k-block).  The
