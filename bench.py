@@ -589,8 +589,11 @@ def main():
     step_tflop = algorithmic_tflop(n_tok, nl + ns)
     step_tflop_a = algorithmic_tflop(N_TXT + N_IMG, nl + ns)
     steps_per_s = args.gpus * K / (ms / 1e3)
-    tot_ms = sum(v["ms"] for v in prof.values())
-    dom_name, dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    # the LoRA down-projections run on a forked stream, on two reserved TPCs, UNDER the other streams' GEMMs
+    # (csrc/dit.cu): their launch durations overlap those GEMMs and are not part of the step's critical path
+    forked = {"lora_down"} if (args.lora_mode == "exact" and os.environ.get("RF_SIDE_STREAM", "1") != "0") else set()
+    tot_ms = sum(v["ms"] for k, v in prof.items() if k not in forked)
+    dom_name, dom = max(((k, v) for k, v in prof.items() if k not in forked), key=lambda kv: kv[1]["ms"])
     ach = dom["flops"] / (dom["ms"] / 1e3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -606,9 +609,13 @@ def main():
                 "launches_per_step": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
                 "share_of_step": dom["ms"] / tot_ms,
                 "how": "CUDA events around every launch of one eager headline forward inside this run"}
-    kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / tot_ms, 4),
+    kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
+                   "share": None if k in forked else round(v["ms"] / tot_ms, 4),
                    "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] else None,
                    "gbs": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1)} for k, v in prof.items()}
+    for k in forked & set(kernels):
+        kernels[k]["note"] = ("forked stream: 4 CTAs on two reserved TPCs, concurrent with the image + text GEMM of the "
+                              "same layer; its duration is hidden, not a share of the step")
     line = {"metric": "denoise-steps/sec", "value": steps_per_s, "unit": "denoise-steps/s",
             "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

@@ -14,7 +14,7 @@ cfg = FluxDiTConfig(num_layers=int(layers[0]), num_single_layers=int(layers[1]))
 use_lora = os.environ.get("LORA", "1") == "1"
 pipe = B200FluxPipeline.from_synthetic(cfg, seed=0, device=dev, lora_rank=32 if use_lora else 0)
 if use_lora:
-    pipe.transformer.load_lora(synthetic_lora(cfg), mode=os.environ.get("LORA_MODE", "merged"))
+    pipe.transformer.load_lora(synthetic_lora(cfg), mode=os.environ.get("LORA_MODE", "exact"))
 g = torch.Generator().manual_seed(0)
 lat = torch.randn(1, 4096, 64, generator=g).to(torch.bfloat16)
 txt = torch.randn(1, 512, 4096, generator=g).to(torch.bfloat16)

@@ -7,7 +7,7 @@ CMD="python bench.py --steps 2 --warmup 1 --no-tree --no-eager --no-cpu-baseline
 # warm-up step + e2e etc. come later in bench.py; the first ~450 launches after pipeline build are the warm-up step,
 # the next ~900 the two timed steps: capture a window that covers them
 # (only this library's kernels: the synthetic-weight initialisation launches thousands of torch kernels first)
-KN='regex:^(gemm2_kernel|gemm_kernel|attn_kernel|ln_modulate_kernel|lora_down_kernel|gemv_kernel|select_row_kernel|euler_step_kernel|advance_step_kernel|add2_kernel|add3_kernel|timestep_embed_kernel|f32_to_bf16_kernel)$'
+KN='regex:^(gemm2_kernel|gemm_kernel|attn_kernel|ln_modulate_kernel|lora_down_kernel|lora_down_side_kernel|gemv_kernel|select_row_kernel|euler_step_kernel|advance_step_kernel|add2_kernel|add3_kernel|timestep_embed_kernel|f32_to_bf16_kernel)$'
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     -k "$KN" -c 1800 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/r02_launches.log 2>&1
 echo "launch list rc=$?"
