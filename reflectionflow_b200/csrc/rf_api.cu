@@ -31,6 +31,7 @@ struct ProfRec {
 };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
+bool prof_on() { return g_prof_on; }
 ProfScope::ProfScope(const char* name, double flops, double bytes, cudaStream_t s)
     : idx(-1), stream(s) {
   if (!g_prof_on) return;

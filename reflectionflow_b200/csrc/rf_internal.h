@@ -50,6 +50,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // Optional per-launch timing (rf_profile_start/stop): CUDA events around every kernel launch on
 // the launching stream, aggregated per kernel name with its algorithmic FLOPs / bytes.
+bool prof_on();  // rf_profile_start() is active: per-launch events are being recorded (graphs are bypassed)
 struct ProfScope {
   ProfScope(const char* name, double flops, double bytes, cudaStream_t stream);
   ~ProfScope();

@@ -369,6 +369,24 @@ struct rf_vae {
   bf16 *tok = nullptr, *tokx = nullptr, *qkv = nullptr, *S = nullptr, *vt = nullptr, *ao = nullptr, *ay = nullptr;
   float* gn_acc = nullptr;  // [kGnBlocks][2 * C/4] block partials
   float* gn_mr = nullptr;
+  // ---- captured graphs: one decode / encode = ~150 launches whose tensor maps are encoded on the host, which made
+  // the call host-bound (22 ms for 16 ms of kernels at 1024x1024).  The launch sequence of a geometry is captured
+  // once on `own_stream` against staging buffers and replayed; RF_VAE_GRAPH=0 and profiling runs stay eager.
+  struct Graph {
+    int kind, height, width;            // kind 0 decode, 1 encode
+    float scale, shift;
+    int flags;                          // decode: 1 = u8 out, 2 = bf16 out; encode: 1 = u8 in, 2 = bf16 in, 4 = eps
+    cudaGraphExec_t exec;
+    long long tag_end[4];
+    int64_t launches;
+  };
+  std::vector<Graph> graphs;
+  cudaStream_t own_stream = nullptr;    // capture is illegal on the legacy default stream
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  uint8_t* g_u8 = nullptr;              // [H, W, 3] image staging (decode output / encode input)
+  bf16* g_chw = nullptr;                // [3, H, W]
+  bf16* g_lat = nullptr;                // packed latents [(H/16)(W/16), 64]
+  bf16* g_eps = nullptr;                // [16, H/8, W/8]
 };
 
 namespace {
@@ -468,9 +486,23 @@ int conv(rf_vae* h, const ConvW& c, const bf16* in, bf16* out, const bf16* res, 
   return rf::conv_launch(in, c.w, c.b, out, res, h->ones, H, W, c.cin_pad, c.cout_pad, c.taps, 1, s);
 }
 
+void drop_graphs(rf_vae* h) {
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
 int ensure_workspace(rf_vae* h, int H, int W) {  // H, W: output image size
   if (h->ws_h >= H && h->ws_w >= W && h->buf[0]) return 0;
+  drop_graphs(h);  // they reference the old workspace
   const int lh = H / 8, lw = W / 8;
+  {
+    void* q;
+    RF_TRYV(valloc(h, &q, static_cast<size_t>(H) * W * 3)); h->g_u8 = static_cast<uint8_t*>(q);
+    RF_TRYV(valloc(h, &q, static_cast<size_t>(H) * W * 3 * 2)); h->g_chw = static_cast<bf16*>(q);
+    RF_TRYV(valloc(h, &q, static_cast<size_t>(H / 16) * (W / 16) * 64 * 2)); h->g_lat = static_cast<bf16*>(q);
+    RF_TRYV(valloc(h, &q, static_cast<size_t>(lh) * lw * 16 * 2)); h->g_eps = static_cast<bf16*>(q);
+  }
   // largest padded tensor: full resolution x 256 channels (input of up_blocks.2's upsampler conv)
   const size_t big = padded_elems(H, W, 256);
   void* p;
@@ -571,9 +603,82 @@ int mid_block(rf_vae* h, const MidBlock& m, int& x, int& y, int t1, int t2, int 
   return 0;
 }
 
+bool use_graphs() {
+  const char* e = getenv("RF_VAE_GRAPH");
+  return !(e && atoi(e) == 0) && !rf::prof_on();
+}
+// work stream of the graph path: the caller's work is ordered before it by an event
+int graph_stream(rf_vae* h, cudaStream_t caller, cudaStream_t* s) {
+  if (!h->own_stream) {
+    RF_CHECK_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    RF_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    RF_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+  }
+  RF_CHECK_CUDA(cudaEventRecord(h->ev_in, caller));
+  RF_CHECK_CUDA(cudaStreamWaitEvent(h->own_stream, h->ev_in, 0));
+  *s = h->own_stream;
+  return 0;
+}
+// replay the graph of (kind, geometry, factors, flags), capturing `body` first if it does not exist yet.  The
+// capture starts from "no zero ring valid", so a replay re-establishes every ring it relies on, whatever ran before.
+template <typename Body>
+int run_graph(rf_vae* h, int kind, int height, int width, float scale, float shift, int flags, cudaStream_t s,
+              Body&& body) {
+  rf_vae::Graph* g = nullptr;
+  for (auto& c : h->graphs)
+    if (c.kind == kind && c.height == height && c.width == width && c.scale == scale && c.shift == shift &&
+        c.flags == flags)
+      g = &c;
+  if (!g) {
+    for (int i = 0; i < 4; ++i) h->tag[i] = -1;
+    cudaGraph_t graph = nullptr;
+    const int64_t before = rf::launch_count();
+    RF_CHECK_CUDA(cudaStreamSynchronize(s));
+    RF_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int erc = body();
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    const int64_t launches = rf::launch_count() - before;
+    rf::count_launch(static_cast<int>(-launches));  // captured, not executed
+    if (erc || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      for (int i = 0; i < 4; ++i) h->tag[i] = -1;
+      if (!erc) {
+        rf::set_error(std::string("rf_vae: graph capture failed: ") + cudaGetErrorString(ce));
+        erc = -2;
+      }
+      return erc;
+    }
+    rf_vae::Graph ng{kind, height, width, scale, shift, flags, nullptr, {0, 0, 0, 0}, launches};
+    ce = cudaGraphInstantiate(&ng.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      for (int i = 0; i < 4; ++i) h->tag[i] = -1;
+      rf::set_error(std::string("rf_vae: cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+      return -2;
+    }
+    for (int i = 0; i < 4; ++i) ng.tag_end[i] = h->tag[i];
+    if (h->graphs.size() >= 8) {  // a handful of geometries in practice (decode 1024, encode 512)
+      if (h->graphs.front().exec) cudaGraphExecDestroy(h->graphs.front().exec);
+      h->graphs.erase(h->graphs.begin());
+    }
+    h->graphs.push_back(ng);
+    g = &h->graphs.back();
+  }
+  RF_CHECK_CUDA(cudaGraphLaunch(g->exec, s));
+  rf::count_launch(static_cast<int>(g->launches));
+  for (int i = 0; i < 4; ++i) h->tag[i] = g->tag_end[i];
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+static int decode_body(rf_vae* h, const void* packed_latents, int height, int width, float scaling_factor,
+                       float shift_factor, uint8_t* out_u8_hwc, void* out_bf16_chw, cudaStream_t s);
+static int encode_body(rf_vae* h, const uint8_t* image_u8_hwc, const void* image_bf16_chw, int height, int width,
+                       const void* eps_bf16_chw, float scaling_factor, float shift_factor, void* packed_out,
+                       cudaStream_t s);
 
 int rf_vae_create(rf_vae** out) {
   if (!out) {
@@ -640,6 +745,10 @@ int rf_vae_create(rf_vae** out) {
 
 void rf_vae_destroy(rf_vae* h) {
   if (!h) return;
+  drop_graphs(h);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -712,9 +821,30 @@ int rf_vae_decode(rf_vae* h, const void* packed_latents, int height, int width, 
       return -1;
     }
   }
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   RF_TRYV(ensure_workspace(h, height, width));
   if (vae_missing(h, "decoder.") != 0) return -4;
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  if (!use_graphs()) return decode_body(h, packed_latents, height, width, scaling_factor, shift_factor, out_u8_hwc,
+                                        out_bf16_chw, caller);
+  cudaStream_t s = nullptr;
+  RF_TRYV(graph_stream(h, caller, &s));
+  const size_t lat_bytes = static_cast<size_t>(height / 16) * (width / 16) * 64 * 2;
+  RF_CHECK_CUDA(cudaMemcpyAsync(h->g_lat, packed_latents, lat_bytes, cudaMemcpyDeviceToDevice, s));
+  const int flags = (out_u8_hwc ? 1 : 0) | (out_bf16_chw ? 2 : 0);
+  RF_TRYV(run_graph(h, 0, height, width, scaling_factor, shift_factor, flags, s, [&]() {
+    return decode_body(h, h->g_lat, height, width, scaling_factor, shift_factor, out_u8_hwc ? h->g_u8 : nullptr,
+                       out_bf16_chw ? h->g_chw : nullptr, s);
+  }));
+  const size_t px = static_cast<size_t>(height) * width * 3;
+  if (out_u8_hwc) RF_CHECK_CUDA(cudaMemcpyAsync(out_u8_hwc, h->g_u8, px, cudaMemcpyDeviceToDevice, s));
+  if (out_bf16_chw) RF_CHECK_CUDA(cudaMemcpyAsync(out_bf16_chw, h->g_chw, px * 2, cudaMemcpyDeviceToDevice, s));
+  RF_CHECK_CUDA(cudaEventRecord(h->ev_out, s));
+  RF_CHECK_CUDA(cudaStreamWaitEvent(caller, h->ev_out, 0));
+  return 0;
+}
+
+static int decode_body(rf_vae* h, const void* packed_latents, int height, int width, float scaling_factor,
+                       float shift_factor, uint8_t* out_u8_hwc, void* out_bf16_chw, cudaStream_t s) {
   int H = height / 8, W = width / 8;
   int x = 0, y = 1;
   const int t1 = 2, t2 = 3;
@@ -784,9 +914,33 @@ int rf_vae_encode(rf_vae* h, const uint8_t* image_u8_hwc, const void* image_bf16
       return -1;
     }
   }
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   RF_TRYV(ensure_workspace(h, height, width));
   if (vae_missing(h, "encoder.") != 0) return -4;
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  if (!use_graphs()) return encode_body(h, image_u8_hwc, image_bf16_chw, height, width, eps_bf16_chw, scaling_factor,
+                                        shift_factor, packed_out, caller);
+  cudaStream_t s = nullptr;
+  RF_TRYV(graph_stream(h, caller, &s));
+  const size_t px = static_cast<size_t>(height) * width * 3;
+  if (image_u8_hwc) RF_CHECK_CUDA(cudaMemcpyAsync(h->g_u8, image_u8_hwc, px, cudaMemcpyDeviceToDevice, s));
+  else RF_CHECK_CUDA(cudaMemcpyAsync(h->g_chw, image_bf16_chw, px * 2, cudaMemcpyDeviceToDevice, s));
+  const size_t eps_bytes = static_cast<size_t>(height / 8) * (width / 8) * 16 * 2;
+  if (eps_bf16_chw) RF_CHECK_CUDA(cudaMemcpyAsync(h->g_eps, eps_bf16_chw, eps_bytes, cudaMemcpyDeviceToDevice, s));
+  const int flags = (image_u8_hwc ? 1 : 2) | (eps_bf16_chw ? 4 : 0);
+  RF_TRYV(run_graph(h, 1, height, width, scaling_factor, shift_factor, flags, s, [&]() {
+    return encode_body(h, image_u8_hwc ? h->g_u8 : nullptr, image_u8_hwc ? nullptr : h->g_chw, height, width,
+                       eps_bf16_chw ? h->g_eps : nullptr, scaling_factor, shift_factor, h->g_lat, s);
+  }));
+  RF_CHECK_CUDA(cudaMemcpyAsync(packed_out, h->g_lat, static_cast<size_t>(height / 16) * (width / 16) * 64 * 2,
+                                cudaMemcpyDeviceToDevice, s));
+  RF_CHECK_CUDA(cudaEventRecord(h->ev_out, s));
+  RF_CHECK_CUDA(cudaStreamWaitEvent(caller, h->ev_out, 0));
+  return 0;
+}
+
+static int encode_body(rf_vae* h, const uint8_t* image_u8_hwc, const void* image_bf16_chw, int height, int width,
+                       const void* eps_bf16_chw, float scaling_factor, float shift_factor, void* packed_out,
+                       cudaStream_t s) {
   int H = height, W = width;
   int x = 0, y = 1;
   const int t1 = 2, t2 = 3;

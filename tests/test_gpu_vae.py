@@ -77,6 +77,34 @@ def test_encode_matches_oracle(height, width, use_eps):
     assert d.mean() <= 3.0 * e_ref.mean() + 2e-3
 
 
+def test_captured_graphs_replay_the_eager_bits(monkeypatch):
+    """rf_vae_decode / rf_vae_encode capture their launch sequence per geometry and replay it (csrc/vae.cu).  A replay
+    must give the bits of the eager sequence whatever ran in between: decode 256x256, encode 128x512 (other geometry,
+    same workspace buffers, different zero rings), decode 256x256 again (replay), then the same calls eagerly
+    (RF_VAE_GRAPH=0)."""
+    _, ours = _models()
+    g = torch.Generator().manual_seed(5)
+    lat_a = torch.randn(1, 16 * 16, 64, generator=g).to(torch.bfloat16)
+    lat_b = torch.randn(1, 16 * 16, 64, generator=g).to(torch.bfloat16)
+    img = torch.randint(0, 256, (1, 128, 512, 3), generator=g, dtype=torch.uint8)
+    eps = torch.randn(16, 16, 64, generator=g).to(torch.bfloat16)
+
+    def sequence():
+        outs = [ours.decode_packed(lat_a, 256, 256, "u8").clone(), ours.encode_packed(img, eps=eps).clone(),
+                ours.decode_packed(lat_b, 256, 256, "u8").clone(), ours.decode_packed(lat_a, 256, 256, "pt").clone(),
+                ours.encode_packed(img).clone(), ours.decode_packed(lat_a, 256, 256, "u8").clone()]
+        torch.cuda.synchronize()
+        return outs
+
+    monkeypatch.setenv("RF_VAE_GRAPH", "1")
+    graphed = sequence()
+    monkeypatch.setenv("RF_VAE_GRAPH", "0")
+    eager = sequence()
+    for i, (a, b) in enumerate(zip(graphed, eager)):
+        assert torch.equal(a, b), f"call {i} differs between the graph replay and the eager launch sequence"
+    assert torch.equal(graphed[0], graphed[5]) and not torch.equal(graphed[0], graphed[2])
+
+
 def test_postprocess_is_bit_exact_on_given_image():
     """the uint8 conversion itself (x/2+0.5 in bf16, clamp, *255, round-half-even) is exact: feed the
     oracle's own pre-quantisation image through the same formula"""

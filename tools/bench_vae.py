@@ -16,7 +16,19 @@ for _ in range(5):
     out = vae.decode_packed(lat, H, W, "u8")
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print(json.dumps({"vae_decode_ms": ms, "tflops": 10.47 / ms * 1e3, "mean_u8": float(out.float().mean())}))
+res = {"vae_decode_ms": ms, "tflops": 10.47 / ms * 1e3, "mean_u8": float(out.float().mean()),
+       "graph": os.environ.get("RF_VAE_GRAPH", "1")}
+# encode of the 512x512 condition image (the tree's parent -> condition path)
+img = torch.randint(0, 256, (1, 512, 512, 3), dtype=torch.uint8).cuda()
+for _ in range(2):
+    vae.encode_packed(img)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(5):
+    vae.encode_packed(img)
+e1.record(); torch.cuda.synchronize()
+res["vae_encode_512_ms"] = e0.elapsed_time(e1) / 5
+print(json.dumps(res))
 L.profile_start()
 vae.decode_packed(lat, H, W, "u8")
 prof = L.profile_stop()
