@@ -220,3 +220,24 @@ def test_candidate_png_is_encoded_once():
     import io
     assert np.array_equal(np.asarray(Image.open(io.BytesIO(b1))), np.asarray(img))
     assert Candidate("y", 0).png_bytes() is None
+
+
+def test_bench_accounting_matches_the_survey():
+    """bench.py's work counts are the ones SURVEY.md §8(d) / BASELINE.md quote (the judge recomputes TFLOP/s from
+    them): 57 (24 D^2 N + 4 N^2 D), entry A N = 4608 -> 74.385 TFLOP, entry B N = 5632 -> 94.954 TFLOP; and the
+    roofline denominator comes from the driver-written MEASURED_PEAKS.json when it is there."""
+    import importlib.util, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("rf_bench", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert (b.N_TXT, b.N_IMG, b.N_COND) == (512, 4096, 1024)
+    assert abs(b.algorithmic_tflop(4608) - 74.385) < 0.05
+    assert abs(b.algorithmic_tflop(5632) - 94.954) < 0.05
+    assert abs(b.algorithmic_tflop(768) - 10.348) < 0.03  # the survey adds ~0.02 TFLOP of embedders / modulation
+    pk = b.peaks()
+    mp = os.path.join(root, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        m = json.load(open(mp))
+        assert pk["tflops_sustained"] == m["bf16_tflops_sustained"] and "measured" in pk["source"]
+    assert b.physical_cores() >= 1
