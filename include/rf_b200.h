@@ -60,7 +60,9 @@ int rf_op_linear(int epilogue, int M, int N, int K, const void* x, int ldx, cons
  * factors, RF_EPI_QKV); lora_B: [N, 64] (rank zero-padded).  M >= 128, N % 128 == 0, K % 64 == 0;
  * epilogues GELU / GATE_RES / QKV.  workspace: rf_op_linear_lora_workspace_bytes(M) bytes of device
  * memory, zero-initialised once by the caller (split-K partials, the bf16 down-projection and the
- * reduction counters live there). */
+ * reduction counters live there).  The down-projection runs as one chip-filling split-K launch; the
+ * environment switch RF_LORA_DOWN=side selects the four-CTA full-K kernel that rf_dit_forward /
+ * rf_dit_denoise fork under their main GEMM (same result up to the fp32 summation order). */
 size_t rf_op_linear_lora_workspace_bytes(int M);
 int rf_op_linear_lora(int epilogue, int M, int N, int K, const void* x, int ldx, const void* W,
                       const void* bias, void* y, int ldy, const void* lora_A, int t_cols,
