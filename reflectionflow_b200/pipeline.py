@@ -354,17 +354,31 @@ class B200FluxPipeline:
         return self._finish(latents, height, width, output_type, return_dict)
 
 
+def get_config(config_path: str = None) -> dict:
+    """train_flux/flux/generate.py:16-22: the yaml named by `config_path`, else by $XFL_CONFIG, else {}."""
+    import os
+    config_path = config_path or os.environ.get("XFL_CONFIG")
+    if not config_path:
+        return {}
+    import yaml
+    with open(config_path, "r") as f:
+        return yaml.safe_load(f) or {}
+
+
+def seed_everything(seed: int = 42):
+    """train_flux/flux/generate.py:68-72 (the cudnn flag has no meaning here: no cuDNN on the path)."""
+    import numpy as np
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+
+
 @torch.no_grad()
 def generate(pipeline: B200FluxPipeline, conditions: List[Condition] = None, config_path: str = None,
              model_config: Optional[Dict[str, Any]] = {}, condition_scale: float = 1.0,
              default_lora: bool = False, image_guidance_scale: float = 1.0, **params):
     """train_flux/flux/generate.py:75-321 (entry B): FluxPipeline.__call__ + one condition stream.
     Same keyword surface (prepare_params, generate.py:25-65); defaults 512x512 / 28 steps / 3.5."""
-    if not model_config and config_path:
-        import yaml
-        with open(config_path) as f:
-            model_config = (yaml.safe_load(f) or {}).get("model", {})
-    model_config = model_config or {}
+    model_config = model_config or get_config(config_path).get("model", {}) or {}
     if image_guidance_scale != 1.0:
         raise NotImplementedError("image_guidance_scale != 1 is broken upstream (SURVEY App. B.3) "
                                   "and unused by the tts path")

@@ -241,3 +241,19 @@ def test_bench_accounting_matches_the_survey():
         m = json.load(open(mp))
         assert pk["tflops_sustained"] == m["bf16_tflops_sustained"] and "measured" in pk["source"]
     assert b.physical_cores() >= 1
+
+
+def test_get_config_follows_the_reference(tmp_path, monkeypatch):
+    """generate.py:16-22: explicit path, else $XFL_CONFIG, else {} ; generate() takes model_config from its "model" key"""
+    from reflectionflow_b200.pipeline import get_config, seed_everything
+    monkeypatch.delenv("XFL_CONFIG", raising=False)
+    assert get_config() == {}
+    y = tmp_path / "c.yaml"
+    y.write_text("model:\n  union_cond_attn: true\n  add_cond_attn: false\ntrain:\n  lr: 1\n")
+    assert get_config(str(y))["model"] == {"union_cond_attn": True, "add_cond_attn": False}
+    monkeypatch.setenv("XFL_CONFIG", str(y))
+    assert get_config()["train"] == {"lr": 1}
+    seed_everything(7)
+    a = torch.rand(3)
+    seed_everything(7)
+    assert torch.equal(a, torch.rand(3))
