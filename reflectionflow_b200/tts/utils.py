@@ -109,3 +109,25 @@ def recover_json_from_output(output: str):
 
 def get_batches(items, batch_size):
     return [items[i:i + batch_size] for i in range(0, len(items), batch_size)]
+
+
+def load_image(path_or_url):
+    """tts/utils.py:188-200: a PIL image is returned as is, "http..." is fetched (needs network), else a local path."""
+    from PIL import Image
+    if isinstance(path_or_url, Image.Image):
+        return path_or_url
+    if str(path_or_url).startswith("http"):
+        import io
+        import requests
+        response = requests.get(path_or_url, stream=True)
+        response.raise_for_status()
+        return Image.open(io.BytesIO(response.content))
+    return Image.open(path_or_url)
+
+
+def convert_to_bytes(path_or_url) -> bytes:
+    """tts/utils.py:203-208: RGB PNG bytes of an image given by object, path or URL."""
+    import io
+    buf = io.BytesIO()
+    load_image(path_or_url).convert("RGB").save(buf, format="PNG")
+    return buf.getvalue()

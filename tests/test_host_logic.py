@@ -257,3 +257,18 @@ def test_get_config_follows_the_reference(tmp_path, monkeypatch):
     a = torch.rand(3)
     seed_everything(7)
     assert torch.equal(a, torch.rand(3))
+
+
+def test_image_helpers_of_tts_utils(tmp_path):
+    """tts/utils.py:188-208"""
+    import io
+    from PIL import Image
+    from reflectionflow_b200.tts.utils import convert_to_bytes, load_image
+    im = Image.new("RGBA", (5, 3), (10, 20, 30, 40))
+    assert load_image(im) is im
+    p = tmp_path / "x.png"
+    im.save(p)
+    assert load_image(str(p)).size == (5, 3)
+    back = Image.open(io.BytesIO(convert_to_bytes(str(p))))
+    assert back.mode == "RGB" and back.format == "PNG" and back.getpixel((0, 0)) == (10, 20, 30)
+    assert convert_to_bytes(im) == convert_to_bytes(str(p))
