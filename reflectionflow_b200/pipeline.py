@@ -354,6 +354,21 @@ class B200FluxPipeline:
         return self._finish(latents, height, width, output_type, return_dict)
 
 
+def encode_images(pipeline: "B200FluxPipeline", images, eps: Optional[torch.Tensor] = None,
+                  generator: Optional[torch.Generator] = None):
+    """Module-level form of train_flux/flux/pipeline_tools.py:7-30 (`encode_images(pipeline, images)`):
+    -> (image tokens [B, (H/16)(W/16), 64], position ids).  The posterior noise is explicit (see the method)."""
+    return pipeline.encode_images(images, eps=eps, generator=generator)
+
+
+def prepare_text_input(pipeline: "B200FluxPipeline", prompts, max_sequence_length: int = 512, prompts_2=None):
+    """train_flux/flux/pipeline_tools.py:33-52: `encode_prompt` with the reference's fixed arguments
+    -> (prompt_embeds, pooled_prompt_embeds, text_ids)."""
+    return pipeline.encode_prompt(prompt=prompts, prompt_2=prompts_2, prompt_embeds=None,
+                                  pooled_prompt_embeds=None, device=pipeline.device, num_images_per_prompt=1,
+                                  max_sequence_length=max_sequence_length, lora_scale=None)
+
+
 def get_config(config_path: str = None) -> dict:
     """train_flux/flux/generate.py:16-22: the yaml named by `config_path`, else by $XFL_CONFIG, else {}."""
     import os

@@ -272,3 +272,26 @@ def test_image_helpers_of_tts_utils(tmp_path):
     back = Image.open(io.BytesIO(convert_to_bytes(str(p))))
     assert back.mode == "RGB" and back.format == "PNG" and back.getpixel((0, 0)) == (10, 20, 30)
     assert convert_to_bytes(im) == convert_to_bytes(str(p))
+
+
+def test_pipeline_tools_module_level_forms():
+    """pipeline_tools.py:7-52: `encode_images(pipeline, images)` and `prepare_text_input(pipeline, prompts, ...)` keep
+    the reference's call shape and hand the reference's fixed arguments to the pipeline"""
+    from reflectionflow_b200 import pipeline as P
+    seen = {}
+
+    class Pipe:
+        device = "cpu"
+
+        def encode_images(self, images, eps=None, generator=None):
+            seen["img"] = (images, eps, generator)
+            return "tokens", "ids"
+
+        def encode_prompt(self, **kw):
+            seen["txt"] = kw
+            return "pe", "pooled", "text_ids"
+
+    assert P.encode_images(Pipe(), "IMG") == ("tokens", "ids") and seen["img"] == ("IMG", None, None)
+    assert P.prepare_text_input(Pipe(), ["a", "b"], max_sequence_length=256) == ("pe", "pooled", "text_ids")
+    assert seen["txt"] == dict(prompt=["a", "b"], prompt_2=None, prompt_embeds=None, pooled_prompt_embeds=None,
+                               device="cpu", num_images_per_prompt=1, max_sequence_length=256, lora_scale=None)
