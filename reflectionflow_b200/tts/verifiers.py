@@ -350,6 +350,52 @@ class OpenAIShapedReflector:
         return self._chat(self.system_message_refine, inputs)
 
 
+class ReflectionGeneratorOurs:
+    """`reflection_args.name` other than "openai" (tts_reflectionflow.py:26-44, 220-238): the fine-tuned
+    Qwen2.5-VL reflection generator behind an OpenAI-compatible server — one
+    `client.chat.completions.create(messages=, model=)` request per selected image, each retried up to
+    `max_retries` times (the reference then silently drops the entry; here the last error is raised, so the list
+    cannot come back short).  Prompt refinement stays with the OpenAI-shaped refiner (:247-254): `refiner`, or
+    the current prompts unchanged when there is none."""
+
+    def __init__(self, client, refiner=None, model_name: str = "Qwen/Qwen2.5-VL-7B-Instruct",
+                 max_retries: int = 5, retry_delay: float = 2.0):
+        self.client, self.refiner, self.model_name = client, refiner, model_name
+        self.max_retries, self.retry_delay = max_retries, retry_delay
+
+    @staticmethod
+    def generate_messages(bad_image: str, prompt: str):
+        """tts_reflectionflow.py:27-41 (`bad_image`: a path or URL the server can read, or a data URL)"""
+        return [{"role": "system", "content": "You are a helpful assistant."},
+                {"role": "user", "content": [
+                    {"type": "image_url", "image_url": {"url": bad_image}},
+                    {"type": "text", "text": "Generate reflections to improve the input image according to the "
+                                             f"prompt. The prompt is: \"{prompt}\""}]}]
+
+    def generate_reflections(self, cands, original_prompt, current_prompts, reflections, evaluations):
+        import time
+        out = []
+        for c in cands:
+            url = c.name if os.path.exists(c.name) else _jpeg_data_url(_images_of([c])[0])
+            messages = self.generate_messages(url, original_prompt)
+            for attempt in range(self.max_retries):
+                try:
+                    res = self.client.chat.completions.create(messages=messages, model=self.model_name)
+                    out.append(res.choices[0].message.content)
+                    break
+                except Exception as e:  # noqa: BLE001 - the reference retries on anything (:231-238)
+                    if attempt + 1 == self.max_retries:
+                        raise
+                    print(f"Error generating reflection: {e}. Retrying in {self.retry_delay} seconds...")
+                    time.sleep(self.retry_delay)
+        return out
+
+    def refine_prompt(self, cands, original_prompt, current_prompts, reflections, evaluations=None):
+        if self.refiner is None:
+            return list(current_prompts)
+        return self.refiner.refine_prompt(cands, original_prompt, current_prompts, reflections, evaluations)
+
+
 class StubReflector:
     """Deterministic reflection writer + prompt refiner (same list-in / list-out shapes as
     OpenAIVerifier.generate_reflections / refine_prompt, openai_verifier.py:241-317)."""

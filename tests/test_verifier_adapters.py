@@ -180,3 +180,44 @@ def test_outer_loop_round_with_the_ours_branch(tmp_path):
     assert len(os.listdir(dirs["best"])) == 1
     line = json.loads(open(os.path.join(tmp, "best_img_detailedscore.jsonl")).readline())
     assert "Overall" in line["evaluation"][0]
+
+
+def test_reflection_generator_ours_messages_and_retries(tmp_path):
+    """tts_reflectionflow.py:26-44, 220-238: one request per image with the reference's two messages; failures are
+    retried; refinement is delegated"""
+    calls, fail = [], {"n": 2}
+
+    class Client:
+        class chat:  # noqa: N801 - mirrors the SDK attribute chain
+            class completions:  # noqa: N801
+                @staticmethod
+                def create(messages, model):
+                    calls.append((messages, model))
+                    if fail["n"] > 0:
+                        fail["n"] -= 1
+                        raise ConnectionError("server busy")
+                    return types.SimpleNamespace(choices=[types.SimpleNamespace(
+                        message=types.SimpleNamespace(content=f"reflection #{len(calls)}"))])
+
+    on_disk = _cand(0, (1, 2, 3))
+    on_disk.name = str(tmp_path / "1_round@5.png")
+    on_disk.pil().save(on_disk.name)
+    in_memory = _cand(1, (4, 5, 6))
+    r = V.ReflectionGeneratorOurs(Client(), retry_delay=0.0)
+    out = r.generate_reflections([on_disk, in_memory], "a blue bird", ["cur"] * 2, [""] * 2, ["{}"] * 2)
+    assert out == ["reflection #3", "reflection #4"] and len(calls) == 4      # two failures retried
+    messages, model = calls[-2]
+    assert model == "Qwen/Qwen2.5-VL-7B-Instruct" and messages[0] == {"role": "system",
+                                                                     "content": "You are a helpful assistant."}
+    assert messages[1]["content"][0] == {"type": "image_url", "image_url": {"url": on_disk.name}}
+    assert messages[1]["content"][1]["text"] == ("Generate reflections to improve the input image according to the "
+                                                 'prompt. The prompt is: "a blue bird"')
+    assert calls[-1][0][1]["content"][0]["image_url"]["url"].startswith("data:image/jpeg;base64,")
+    assert r.refine_prompt([on_disk], "p", ["cur"], out[:1]) == ["cur"]         # no refiner: prompts unchanged
+    inner = V.StubReflector()
+    assert V.ReflectionGeneratorOurs(Client(), refiner=inner).refine_prompt([on_disk], "p", ["cur"], out[:1]) == \
+        inner.refine_prompt([on_disk], "p", ["cur"], out[:1])
+    fail["n"] = 99
+    with pytest.raises(ConnectionError):
+        V.ReflectionGeneratorOurs(Client(), max_retries=2, retry_delay=0.0).generate_reflections(
+            [in_memory], "p", ["c"], [""], ["{}"])
