@@ -169,3 +169,43 @@ def global_best(chains: Dict[str, dict], verifier_name: str) -> str:
     allv = [(l, s, n) for c in chains.values()
             for n, l, s in zip(c["images"], c["labels"], c["scores"])]
     return sorted(allv, key=lambda x: (0 if x[0] == "yes" else 1, -x[1] if x[0] == "yes" else x[1]))[0][2]
+
+
+# ---- parsers for the reflection generator's sectioned text (tts_reflectionflow.py:48-90; defined upstream but not
+# called by the shipped loop — kept for callers that post-process reflections the same way)
+def _reflection_items(content: str) -> List[str]:
+    return [part.strip() for part in content.split("\n-") if part.strip()]
+
+
+def extract_reflections(reflections: Sequence[str]) -> List[Dict[str, List[str]]]:
+    """"<k>. <Title>:  <item>\\n- <item>..." sections separated by blank lines -> {title: [items]} per reflection
+    (a section counts only if it has the colon + two spaces separator, :55-62)."""
+    results = []
+    for text in reflections:
+        parsed: Dict[str, List[str]] = {}
+        for section in text.split("\n\n"):
+            if ":  " not in section:
+                continue
+            head, content = section.split(":  ", 1)
+            parsed[head.split(". ", 1)[1].strip()] = _reflection_items(content)
+        results.append(parsed)
+    return results
+
+
+def concat_extract_reflections(reflections: Sequence[str]) -> List[str]:
+    """the items of every section joined by blanks, sections whose items mention "None" dropped, sections
+    concatenated without a separator (:66-90)."""
+    results = []
+    for text in reflections:
+        joined = ""
+        for section in text.split("\n\n"):
+            if ":" not in section:
+                continue
+            head, content = section.split(":", 1)
+            head.split(".", 1)[1]  # the reference indexes the numbered title here too: un-numbered titles raise
+            items = _reflection_items(content)
+            if any("None" in item for item in items):
+                continue
+            joined += " ".join(items)
+        results.append(joined)
+    return results

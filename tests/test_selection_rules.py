@@ -95,3 +95,17 @@ def test_records_roundtrip_and_sharding():
     assert len(b) == S.RECORD_BYTES and S.unpack_record(b) == (5, 2 ** 31 - 2, 1, 0.123456789)
     assert S.shard_candidates(8, 1, 4) == [1, 5] and S.shard_candidates(3, 2, 4) == [2]
     assert sorted(sum((S.shard_candidates(7, r, 3) for r in range(3)), [])) == list(range(7))
+
+
+def test_reflection_text_parsers():
+    """tts_reflectionflow.py:48-90"""
+    from reflectionflow_b200.tts import search as S
+    text = ("1. Object:  add a second dog\n- make it brown\n\n"
+            "2. Position:  None\n\n"
+            "3. Style:  sharper focus\n\nfree text without a title")
+    assert S.extract_reflections([text, ""]) == [
+        {"Object": ["add a second dog", "make it brown"], "Position": ["None"], "Style": ["sharper focus"]}, {}]
+    assert S.concat_extract_reflections([text]) == ["add a second dog make it brownsharper focus"]
+    import pytest
+    with pytest.raises(IndexError):
+        S.concat_extract_reflections(["Title: no number"])
