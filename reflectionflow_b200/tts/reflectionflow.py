@@ -164,10 +164,20 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
     reflection_performed = refinement_performed = False
     update_reflections, refined_prompt = None, None
     evaluations = [json.dumps(o) for o in selected_outputs]
+    # LLM hooks that look at the images (everything but the stub) need the selected parents' pixels on rank 0,
+    # whichever rank generated them and whether or not the verifier needed pixels
+    wants_pixels = getattr(reflector, "needs_images", not isinstance(reflector, StubReflector))
+
+    def hook_pixels():
+        if wants_pixels:
+            for c in selected:
+                _ensure_pixels(pipe, c, pa["height"], pa["width"])
+                c.pil()
     if reflection_args and reflection_args.get("run_reflection", False):
         t0 = time.time()
         def reflect():
             retries = 0
+            hook_pixels()
             while True:
                 try:
                     return reflector.generate_reflections(
@@ -185,9 +195,11 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str,
     prompt_refiner_args = config_cp.get("prompt_refiner_args", None)
     if prompt_refiner_args and prompt_refiner_args.get("run_refinement", False):
         t0 = time.time()
-        refined_prompt = _rank0_call(ctx, lambda: reflector.refine_prompt(
-            selected, original_prompt, updated_prompt, update_reflections,
-            evaluations if verifier_name == "openai" else None))
+        def refine():
+            hook_pixels()
+            return reflector.refine_prompt(selected, original_prompt, updated_prompt, update_reflections,
+                                           evaluations if verifier_name == "openai" else None)
+        refined_prompt = _rank0_call(ctx, refine)
         refinement_performed = True
         if rank0:
             print(f"Time taken for prompt refinement: {time.time() - t0} seconds")

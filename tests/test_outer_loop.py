@@ -233,3 +233,42 @@ def test_openai_shaped_outputs_travel_whole(tmp_path):
     assert all("accuracy_to_prompt" in e and e["overall_score"]["explanation"].startswith("overall") for e in ev)
     line = json.loads(open(os.path.join(tmp, "best_img_detailedscore.jsonl")).readline())
     assert "accuracy_to_prompt" in line["evaluation"][0]
+
+
+def test_image_consuming_hooks_get_pixels_of_latent_only_parents(tmp_path, monkeypatch):
+    """An OpenAI-shaped reflection writer / refiner looks at the selected parents' images.  Parents loaded from
+    `*.latent.pt` (round 0) or generated on another rank carry latents only: rank 0 decodes them before the hook,
+    also when the verifier itself did not need pixels (stub / latent-space verifier)."""
+    from tests.test_verifier_adapters import FakeOpenAI
+    from reflectionflow_b200.tts.verifiers import OpenAIShapedReflector
+    decoded = []
+
+    def fake_pixels(pipe, cand, height, width):
+        if cand.image_u8 is None:
+            decoded.append(cand.name)
+            v = cand.latents.float().reshape(-1)[:192]
+            cand.image_u8 = ((v - v.min()) / (v.max() - v.min() + 1e-6) * 255).to(torch.uint8).reshape(8, 8, 3)
+        return cand.image_u8
+    monkeypatch.setattr(RF, "_ensure_pixels", fake_pixels)
+    torch.manual_seed(5)
+    branch = 3
+    g = torch.Generator().manual_seed(1)
+    parents = [Candidate(f"r0/{i}.png", i, latents=torch.randn(1, 16, 64, generator=g).to(torch.bfloat16))
+               for i in range(branch)]
+    tmp = str(tmp_path)
+    dirs = {k: os.path.join(tmp, k) for k in ("last", "best", "bestround", "mid")}
+    for d in dirs.values():
+        os.makedirs(d)
+    client = FakeOpenAI()
+    refl = OpenAIShapedReflector(client, "REFLEX", "REFINE")
+    cfg = dict(CONFIG, search_args={"search_branch": branch, "search_rounds": 2})
+    dp = RF.sample(get_noises(S.MAX_SEED, branch, H, W), "a cat", ["a cat"] * branch, [""] * branch, 1, FakePipe(),
+                   branch, tmp, cfg, dirs["last"], dirs["best"], dirs["bestround"], parents, dirs["mid"], 2, {},
+                   verifier=StubVerifier("nvila"), reflector=refl, ctx=DistCtx(), generate_fn=fake_generate,
+                   condition_fn=fake_condition)
+    assert set(decoded) >= {p.name for p in parents}           # every selected parent was decoded for the hooks
+    assert len(client.create_calls) == 2 * branch               # one reflection + one refinement request per parent
+    assert all(m[1]["content"][-2]["type"] == "image_url" or any(p["type"] == "image_url" for p in m[1]["content"])
+               for _, m in client.create_calls)
+    assert len(dp["reflections"]) == branch and dp["reflections"][0].startswith("[REFLEX] Original prompt: a cat")
+    assert dp["refined_prompt"][0].startswith("[REFINE] Original prompt: a cat")
