@@ -22,7 +22,7 @@ from . import search as S
 from .dist import DistCtx
 from .reflectionflow import _ensure_pixels, _exchange_outputs
 from .utils import parse_cli_args
-from .verifiers import Candidate, StubVerifier, load_verifier
+from .verifiers import Candidate, load_verifier
 
 BUCKETS = (1, 2, 4, 8, 16, 32)
 
