@@ -295,3 +295,62 @@ def test_pipeline_tools_module_level_forms():
     assert P.prepare_text_input(Pipe(), ["a", "b"], max_sequence_length=256) == ("pe", "pooled", "text_ids")
     assert seen["txt"] == dict(prompt=["a", "b"], prompt_2=None, prompt_embeds=None, pooled_prompt_embeds=None,
                                device="cpu", num_images_per_prompt=1, max_sequence_length=256, lora_scale=None)
+
+
+def _reference_functions(relpath, names, extra=None):
+    """the named top-level functions of a reference file, compiled in isolation (the module itself imports packages
+    that are not installed); None when /root/reference is absent (GPU box, CI elsewhere)"""
+    import ast
+    path = os.path.join("/root/reference", relpath)
+    if not os.path.exists(path):
+        return None
+    ns = dict(extra or {})
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return ns
+
+
+def test_small_utils_agree_with_the_reference(tmp_path):
+    """tts/utils.py:157-222: prompt_to_filename, recover_json_from_output, get_batches, load_verifier_prompt — known
+    answers always, and the reference's own functions wherever the reference tree is present"""
+    import hashlib, json, re
+    from reflectionflow_b200.tts import utils as U
+    long_prompt = "A photo of: two cats & a dog!! " * 6
+    assert U.prompt_to_filename("a red cube") == "prompt@a_red_cube_hash@" + hashlib.sha256(b"a red cube").hexdigest()[:8]
+    # upstream arithmetic: max_length - 8 - 7 prompt characters + "prompt@" + "_hash@" + 8 = max_length + 6
+    assert len(U.prompt_to_filename(long_prompt)) == 106 and "__" not in U.prompt_to_filename(long_prompt)
+    assert U.recover_json_from_output('noise {"a": {"b": 1}} trailing') == {"a": {"b": 1}}
+    assert U.get_batches(list(range(5)), 2) == [[0, 1], [2, 3], [4]]
+    (tmp_path / "p.txt").write_text('"""rubric"""\nline')
+    (tmp_path / "p.json").write_text('{"position": "grade"}')
+    assert U.load_verifier_prompt(str(tmp_path / "p.txt")) == "rubric\nline"
+    assert U.load_verifier_prompt(str(tmp_path / "p.json")) == {"position": "grade"}
+    with pytest.raises(ValueError):
+        U.load_verifier_prompt("x.yaml")
+    ref = _reference_functions("tts/utils.py", {"prompt_to_filename", "recover_json_from_output", "get_batches",
+                                                "load_verifier_prompt"},
+                               {"re": re, "hashlib": hashlib, "json": json})
+    if ref is None:
+        pytest.skip("reference tree not present: known-answer part only")
+    for p in ("a red cube", long_prompt, "  ümlaut/слово  ", ""):
+        assert U.prompt_to_filename(p) == ref["prompt_to_filename"](p)
+        assert U.prompt_to_filename(p, 40) == ref["prompt_to_filename"](p, 40)
+    for out in ('x {"k": [1, {"z": 2}]} y', '{"only": true}'):
+        assert U.recover_json_from_output(out) == ref["recover_json_from_output"](out)
+    for n in (1, 2, 7):
+        assert list(U.get_batches(list(range(6)), n)) == list(ref["get_batches"](list(range(6)), n))
+    for f in ("p.txt", "p.json"):
+        assert U.load_verifier_prompt(str(tmp_path / f)) == ref["load_verifier_prompt"](str(tmp_path / f))
+
+
+def test_param_count_is_flux_dev():
+    """11.901 B parameters (double block 339.8 M, single 141.6 M)"""
+    from reflectionflow_b200.config import FluxDiTConfig
+    n = FluxDiTConfig().param_count()
+    assert abs(n / 1e9 - 11.901) < 0.005
+    one_double = FluxDiTConfig(num_layers=1, num_single_layers=0).param_count() - \
+        FluxDiTConfig(num_layers=0, num_single_layers=0).param_count()
+    one_single = FluxDiTConfig(num_layers=0, num_single_layers=1).param_count() - \
+        FluxDiTConfig(num_layers=0, num_single_layers=0).param_count()
+    assert abs(one_double / 1e6 - 339.8) < 0.1 and abs(one_single / 1e6 - 141.6) < 0.1
