@@ -221,3 +221,26 @@ def test_reflection_generator_ours_messages_and_retries(tmp_path):
     with pytest.raises(ConnectionError):
         V.ReflectionGeneratorOurs(Client(), max_retries=2, retry_delay=0.0).generate_reflections(
             [in_memory], "p", ["c"], [""], ["{}"])
+
+
+def test_grading_schemas_equal_the_reference_classes():
+    """openai_verifier.py:23-69: every `Grading*` pydantic class of the reference, field for field and in order (read
+    from the reference source when it is present; the pinned table below otherwise)"""
+    import ast
+    pinned = {None: 6, "single_object": 4, "two_object": 4, "counting": 4, "colors": 4, "position": 4, "color_attr": 4}
+    assert {k: len(v) for k, v in V.GRADING_ASPECTS.items()} == pinned
+    for tag, aspects in V.GRADING_ASPECTS.items():
+        model = V.grading_model(tag)
+        assert tuple(model.model_fields) == tuple(aspects) and aspects[-1] == "overall_score"
+        assert model.__name__ == ("Grading" if tag is None else f"Grading_{tag}")
+        sub = model.model_fields["overall_score"].annotation
+        assert tuple(sub.model_fields) == ("score", "explanation")
+    path = "/root/reference/tts/verifiers/openai_verifier.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present: pinned table only")
+    ref = {}
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.ClassDef) and node.name.startswith("Grading"):
+            tag = node.name[len("Grading_"):] or None
+            ref[tag] = tuple(s.target.id for s in node.body if isinstance(s, ast.AnnAssign))
+    assert ref == {k: tuple(v) for k, v in V.GRADING_ASPECTS.items()}
