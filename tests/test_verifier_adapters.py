@@ -244,3 +244,52 @@ def test_grading_schemas_equal_the_reference_classes():
             tag = node.name[len("Grading_"):] or None
             ref[tag] = tuple(s.target.id for s in node.body if isinstance(s, ast.AnnAssign))
     assert ref == {k: tuple(v) for k, v in V.GRADING_ASPECTS.items()}
+
+
+def test_message_builders_equal_the_reference_methods():
+    """openai_verifier.py:90-118, 166-238, 256-293: the three `prepare_*` methods of the reference's OpenAIVerifier
+    (they do not touch `self`), compiled out of the reference source and fed the same images / strings as the
+    adapters here — the request payloads must be identical, JPEG bytes included."""
+    import ast, base64
+    from io import BytesIO
+    from typing import Union
+    from PIL import Image
+    path = "/root/reference/tts/verifiers/openai_verifier.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    ns = {"Union": Union, "Image": Image, "base64": base64, "BytesIO": BytesIO}
+    want = {"prepare_inputs", "prepare_refine_prompt_inputs", "prepare_reflexion_prompt_inputs"}
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.ClassDef) and node.name == "OpenAIVerifier":
+            for m in node.body:
+                if isinstance(m, ast.FunctionDef) and m.name in want:
+                    exec(compile(ast.Module([m], []), path, "exec"), ns)
+    assert want <= set(ns)
+    cands = [_cand(0, (200, 10, 30)), _cand(1, (5, 90, 250))]
+    images = [c.pil() for c in cands]
+    orig, cur = ["a red cube"] * 2, ["a red cube, studio light", "a red cube on a table"]
+    refl, evals = ["make it redder", "center the cube"], ['{"overall_score": 7}', '{"overall_score": 3}']
+    v = V.OpenAIShapedVerifier(FakeOpenAI(), "rubric")
+    r = V.OpenAIShapedReflector(FakeOpenAI(), "REFLEX", "REFINE")
+    assert v.prepare_inputs(images, orig) == ns["prepare_inputs"](None, images, orig)
+    assert r.prepare_reflexion_prompt_inputs(images, orig, cur, refl, evals) == \
+        ns["prepare_reflexion_prompt_inputs"](None, images, orig, cur, refl, evals)
+    for kw in (dict(images=images, evaluations=evals, current_prompt=cur, reflections=refl),
+               dict(images=images, current_prompt=cur, reflections=refl),          # nvila branch: no evaluations
+               dict(images=images, evaluations=evals, current_prompt=cur),        # noise + prompt search: no reflections
+               dict()):
+        assert r.prepare_refine_prompt_inputs(orig, **kw) == ns["prepare_refine_prompt_inputs"](None, orig, **kw)
+
+
+def test_reflection_generator_messages_equal_the_reference_function():
+    """tts_reflectionflow.py:27-41"""
+    import ast
+    path = "/root/reference/tts/tts_reflectionflow.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    ns = {}
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.FunctionDef) and node.name == "generate_messages":
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    for img, prompt in (("out/00001/midimg/2_round@17.png", 'a "quoted" prompt'), ("data:image/jpeg;base64,AAAA", "x")):
+        assert V.ReflectionGeneratorOurs.generate_messages(img, prompt) == ns["generate_messages"](img, prompt)
