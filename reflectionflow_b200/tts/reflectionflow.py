@@ -335,10 +335,9 @@ def _exchange_outputs(ctx: DistCtx, verifier_name: str, metric: str, cands: List
         if verifier_name == "nvila":
             outs.append({"image_name": cands[cid].name, "label": "yes" if label else "no", "score": score})
         else:
-            o = dict(full[cid])
+            o = dict(full[cid])  # as the verifier returned it (the reference adds nothing, :146-151)
             if float(S.metric_value(o, metric)) != float(score):
                 raise RuntimeError(f"candidate {cid}: score record and verifier output disagree")
-            o.setdefault("image_name", cands[cid].name)
             outs.append(o)
     return outs
 

@@ -86,8 +86,9 @@ class StubVerifier:
         if self.name == "ours":  # scalar reward under choice_of_metric (ImageVerifierOurs shape)
             return {self.choice_of_metric: float(v), "VQ": float(v), "image_name": cand.name}
         s = max(0, min(10, int(round(5 + 60.0 * v))))
-        return {self.choice_of_metric: {"score": s, "explanation": "stub"},
-                "image_name": cand.name}
+        # no "image_name": the reference's OpenAI outputs are the bare pydantic dumps (openai_verifier.py:147), and
+        # `outputs.index` in the top-k rule tells candidates apart by dict equality (App. B.7)
+        return {self.choice_of_metric: {"score": s, "explanation": "stub"}}
 
     def score(self, cands: Sequence[Candidate], prompts: Sequence[str], tag=None) -> List[Dict[str, Any]]:
         return [self.score_one(c, p) for c, p in zip(cands, prompts)]
@@ -215,10 +216,7 @@ class OpenAIShapedVerifier:
         return _map_in_order(call, list(inputs))
 
     def score(self, cands: Sequence[Candidate], prompts: Sequence[str], tag=None):
-        outs = self.score_inputs(self.prepare_inputs(_images_of(cands), list(prompts)), tag=tag)
-        for c, o in zip(cands, outs):
-            o["image_name"] = c.name
-        return outs
+        return self.score_inputs(self.prepare_inputs(_images_of(cands), list(prompts)), tag=tag)
 
 
 class ImageVerifierOurs:

@@ -6,7 +6,8 @@ The reference function is compiled out of its source file with `ast` and run wit
 path), `OpenAIVerifier` (reflections and refined prompts are hashes of exactly the fields the reference hands it),
 `Condition` and `generate` (record their arguments; generated images take their identity from the file they are first
 saved under).  The re-hosted loop gets the same scores and texts through its hooks and a latent-producing fake
-denoiser.  Compared over several rounds with the reference's nvila configuration: the selected parents, the
+denoiser.  Compared over several rounds with the reference's nvila and gptscore configurations (the latter also with
+EQUAL grading dicts for different images, where `outputs.index` collapses them, App. B.7): the selected parents, the
 prompt + " [Reflexion]: " + reflection strings and conditions handed to `generate`, the refined prompts / reflections
 carried to the next round, the chains, `best_img_detailedscore.jsonl` and `best_img_meta.jsonl` byte for byte, and
 which candidate lands in samples_lastround / samples_path_bestround / samples_best.  Needs /root/reference."""
@@ -52,6 +53,16 @@ def _verdict(image_id: str):
     return label, float(np.float32(0.5 + (v % 1000) / 2000.0))
 
 
+def _grading(image_id: str, unique: bool):
+    """the fake GPT grader (openai_verifier.py:122-147 returns the bare model dump): few distinct scores; with
+    `unique=False` the explanations are constant too, so different images get EQUAL dicts — the case in which the
+    reference's `outputs.index` picks the first of them for all (App. B.7)"""
+    v = int(_h("grade", os.path.basename(image_id)), 16)
+    why = f"because {v % 97}" if unique else "ok"
+    return {"accuracy_to_prompt": {"score": v % 3 + 6, "explanation": why},
+            "overall_score": {"score": v % 4 + 4, "explanation": why}}
+
+
 def _reflection(image_id, evaluation, current_prompt, reflection):
     return "fix-" + _h(os.path.basename(image_id), evaluation.replace(image_id, os.path.basename(image_id)),
                        current_prompt, reflection)
@@ -90,6 +101,14 @@ def _reference_sample(world):
             logits = torch.zeros(1, 2)
             logits[0, 0 if label == "yes" else 1] = score
             return label, (logits,)
+
+        @staticmethod
+        def prepare_inputs(images, prompts):
+            return [im.src for im in images]
+
+        @staticmethod
+        def score(inputs, tag=None, max_new_tokens=None):
+            return [_grading(src, world["unique"]) for src in inputs]
 
     class OpenAIVerifier:  # the reference builds its refiner from this name inside sample()
         def __init__(self, **kw):
@@ -131,7 +150,12 @@ def _reference_sample(world):
 class _Verifier:
     needs_images = False
 
+    def __init__(self, kind, unique):
+        self.kind, self.unique = kind, unique
+
     def score(self, cands, prompts, tag=None):
+        if self.kind == "openai":
+            return [_grading(c.name, self.unique) for c in cands]
         out = []
         for c in cands:
             label, score = _verdict(c.name)
@@ -154,8 +178,8 @@ class _Pipe:
     vae = None
 
 
-def _run_reference(tmp, config, rounds, branch, noises_per_round):
-    world = {"saves": [], "generate": []}
+def _run_reference(tmp, config, rounds, branch, noises_per_round, unique):
+    world = {"saves": [], "generate": [], "unique": unique}
     sample = _reference_sample(world)
     dirs = {k: os.path.join(tmp, k) for k in ("last", "best", "bestround", "mid")}
     for d in dirs.values():
@@ -175,7 +199,7 @@ def _run_reference(tmp, config, rounds, branch, noises_per_round):
     return log
 
 
-def _run_ours(tmp, config, rounds, branch, noises_per_round):
+def _run_ours(tmp, config, rounds, branch, noises_per_round, unique):
     dirs = {k: os.path.join(tmp, k) for k in ("last", "best", "bestround", "mid")}
     for d in dirs.values():
         os.makedirs(d)
@@ -201,7 +225,7 @@ def _run_ours(tmp, config, rounds, branch, noises_per_round):
         n_gen = len(calls)
         dp = RF.sample(noises_per_round[rnd - 1], "a photo of a cat", upd, refl, rnd, _Pipe(), branch, tmp, config,
                        dirs["last"], dirs["best"], dirs["bestround"], parents, dirs["mid"], rounds, chains, tag=None,
-                       verifier=_Verifier(), reflector=_Reflector(), ctx=DistCtx(), generate_fn=generate_fn,
+                       verifier=_Verifier(config["verifier_args"]["name"], unique), reflector=_Reflector(), ctx=DistCtx(), generate_fn=generate_fn,
                        condition_fn=condition_fn)
         for c in list(parents) + dp["generated"]:
             by_latent[c.latents.float().sum().item()] = c.name
@@ -219,12 +243,13 @@ def _run_ours(tmp, config, rounds, branch, noises_per_round):
     return log
 
 
+@pytest.mark.parametrize("kind,unique", [("nvila", True), ("openai", True), ("openai", False)])
 @pytest.mark.parametrize("seed", [0, 1, 2])
-def test_reflection_rounds_equal_the_reference_function(tmp_path, seed):
+def test_reflection_rounds_equal_the_reference_function(tmp_path, seed, kind, unique):
     rounds, branch = 4, 4
     config = {"pipeline_args": {"height": H, "width": W, "condition_size": COND, "guidance_scale": 3.5,
                                 "num_inference_steps": 4},
-              "verifier_args": {"name": "nvila"},
+              "verifier_args": {"name": kind},
               "refine_args": {"choice_of_metric": "overall_score", "max_new_tokens": 1280,
                               "refine_prompt_relpath": "r.txt", "reflexion_prompt_relpath": "x.txt",
                               "verifier_prompt_relpath": "v.json"},
@@ -238,10 +263,10 @@ def test_reflection_rounds_equal_the_reference_function(tmp_path, seed):
     try:  # both runs write relative artefact paths under their own directory
         os.makedirs(tmp_path / "ref")
         os.chdir(tmp_path / "ref")
-        ref = _run_reference("run", config, rounds, branch, noises)
+        ref = _run_reference("run", config, rounds, branch, noises, unique)
         os.makedirs(tmp_path / "ours")
         os.chdir(tmp_path / "ours")
-        ours = _run_ours("run", config, rounds, branch, noises)
+        ours = _run_ours("run", config, rounds, branch, noises, unique)
     finally:
         os.chdir(cwd)
     for rnd, (a, b) in enumerate(zip(ref, ours), start=1):
