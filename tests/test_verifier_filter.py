@@ -90,3 +90,69 @@ def test_main_walks_every_prompt_folder(tmp_path):
     with pytest.raises(RuntimeError, match="no candidates"):
         os.makedirs(run / "00002" / "midimg")
         VF.filter_folder(str(run / "00002"), "p", StubVerifier("nvila"))
+
+
+def test_filter_equals_the_reference_main(tmp_path):
+    """tts/verifier_filter.py::main (:28-176), unmodified, compiled out of its file and run over fakes (argument
+    parser, NVILA loader, `Image.open(...).save(...)` recording paths) on the same run directory: the image copied
+    into every nfe<N> folder is the same."""
+    import ast
+    import hashlib
+    import types
+
+    import numpy as np
+    ref_path = "/root/reference/tts/verifier_filter.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference tree not present")
+    run = tmp_path / "run"
+    for i in range(2):
+        f, _ = _make_run(str(tmp_path / f"tmp{i}"), rounds=(1, 2, 3, 10), per_round=5)   # 20 candidates: nfe32 = all
+        os.makedirs(run, exist_ok=True)
+        os.rename(f, run / f"{i:05}")
+    cfg = {"pipeline_args": {"height": 64, "width": 64},
+           "verifier_args": {"name": "nvila", "model_name": "m", "cache_dir": "c"}}
+    (tmp_path / "cfg.json").write_text(json.dumps(cfg))
+
+    def verdict(path):
+        v = int(hashlib.sha256(os.path.basename(path).encode()).hexdigest()[:8], 16)
+        return ("yes" if v % 4 else "no"), float(np.float32(0.5 + (v % 50) / 100.0))   # coarse scores: ties
+
+    saves = []
+
+    class Opened:
+        def __init__(self, path):
+            self.path = path
+
+        def save(self, dest):
+            saves.append((dest, self.path))
+
+    class ImageMod:
+        open = staticmethod(Opened)
+
+    class Nvila:
+        @staticmethod
+        def generate_content(parts):
+            label, score = verdict(parts[0].path)
+            logits = torch.zeros(1, 2)
+            logits[0, 0 if label == "yes" else 1] = score
+            return label, (logits,)
+
+    args = types.SimpleNamespace(pipeline_config_path=str(tmp_path / "cfg.json"), imgpath=str(run), start_index=0,
+                                 end_index=-1)
+    ns = dict(torch=torch, json=json, os=os, time=__import__("time"), Image=ImageMod, tqdm=lambda it, **kw: it,
+              parse_cli_args=lambda: args, load_model=lambda model_name, cache_dir: (Nvila, 0, 1))
+    fn = next(n for n in ast.parse(open(ref_path).read()).body if isinstance(n, ast.FunctionDef) and n.name == "main")
+    exec(compile(ast.Module([fn], []), ref_path, "exec"), ns)
+    ns["main"]()
+    ref_choice = {(os.path.basename(os.path.dirname(os.path.dirname(d))), os.path.basename(os.path.dirname(d))): s
+                  for d, s in saves}
+
+    class Ours(StubVerifier):
+        def score_one(self, cand, prompt):
+            label, score = verdict(cand.name)
+            return {"image_name": cand.name, "label": label, "score": score}
+
+    for i in range(2):
+        res = VF.filter_folder(str(run / f"{i:05}"), "a photo of a bench", Ours("nvila"), ctx=DistCtx())
+        for n in VF.BUCKETS:
+            assert res["chosen"][n] + ".png" == ref_choice[(f"{i:05}", f"nfe{n}")], (i, n)
