@@ -28,7 +28,10 @@ from .config import FluxDiTConfig
 from .scheduler import FlowMatchEulerDiscreteScheduler, calculate_shift
 from .transformer import B200FluxTransformer2DModel
 
-condition_dict = {"cot": 12}  # train_flux/flux/condition.py:10-21 (only the type the tts path uses)
+# train_flux/flux/condition.py:10-21.  The tts path uses "cot"; the DiT treats every type alike (the type-id column is
+# produced but not consumed, transformer.py:133), so the other types only differ in how `raw_img` becomes the condition.
+condition_dict = {"depth": 0, "canny": 1, "subject": 4, "coloring": 6, "deblurring": 7, "depth_pred": 8, "fill": 9,
+                  "sr": 10, "cartoon": 11, "cot": 12}
 
 
 @dataclass
@@ -58,14 +61,39 @@ class Condition:
         assert mask is None, "Mask not supported yet"
         assert raw_img is not None or condition is not None or latents is not None
         self.condition_type = condition_type
-        self.condition = condition if condition is not None else raw_img
+        self.condition = condition
+        if raw_img is not None:
+            self.condition = self.get_condition(condition_type, raw_img)
         self.position_delta = position_delta
         self.latents = latents
         self.eps, self.generator = eps, generator  # posterior noise of the VAE encode (explicit)
 
+    def get_condition(self, condition_type: str, raw_img):
+        """condition.py:43-80: raw image -> condition image.  "depth" needs the depth-anything network (not reachable
+        offline); for "cot" / "sr" / "depth_pred" the reference has no rule (pass `condition=`): the image is taken as is."""
+        if condition_type == "depth":
+            raise NotImplementedError('"depth" conditions need the depth-estimation model (condition.py:49-59); '
+                                      "pass the depth map as condition=")
+        if condition_type == "canny":
+            import cv2
+            from PIL import Image
+            return Image.fromarray(cv2.Canny(np.array(raw_img), 100, 200)).convert("RGB")
+        if condition_type == "coloring":
+            return raw_img.convert("L").convert("RGB")
+        if condition_type == "deblurring":
+            from PIL import ImageFilter
+            return raw_img.convert("RGB").filter(ImageFilter.GaussianBlur(10)).convert("RGB")
+        if condition_type in ("fill", "cartoon"):
+            return raw_img.convert("RGB")
+        return raw_img  # "subject" (:65-66) and the types without a rule
+
     @property
     def type_id(self) -> int:
         return condition_dict[self.condition_type]
+
+    @classmethod
+    def get_type_id(cls, condition_type: str) -> int:
+        return condition_dict[condition_type]
 
     def encode(self, pipe: "B200FluxPipeline", empty: bool = False):
         if self.latents is not None:
@@ -75,6 +103,8 @@ class Condition:
         else:
             tokens, ids = pipe.encode_images(self.condition, eps=self.eps, generator=self.generator)
         ids = ids.clone()
+        if self.position_delta is None and self.condition_type == "subject" and self.condition is not None:
+            self.position_delta = [0, -self.condition.size[0] // 16]  # condition.py:123-124
         if self.position_delta is not None:
             ids[:, 1] += self.position_delta[0]
             ids[:, 2] += self.position_delta[1]

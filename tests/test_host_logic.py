@@ -112,7 +112,8 @@ def test_generate_entry_b_condition_ids_and_defaults():
         generate(pipe, conditions=[cond, cond], prompt_embeds=e, pooled_prompt_embeds=p,
                  output_type="latent")
     with pytest.raises(NotImplementedError):
-        Condition("depth", latents=cond_lat)
+        Condition("no_such_type", latents=cond_lat)
+    assert Condition("depth", latents=cond_lat).type_id == 0  # every type of condition.py:10-21 runs the same path
     # defaults: 512 x 512 like generate.py:28-29
     generate(pipe, conditions=None, prompt_embeds=e, pooled_prompt_embeds=p, output_type="latent")
     assert ft.calls[-1]["latents"].shape == (1, 1024, 64) and ft.calls[-1]["cond"] is None
@@ -354,3 +355,59 @@ def test_param_count_is_flux_dev():
     one_single = FluxDiTConfig(num_layers=0, num_single_layers=1).param_count() - \
         FluxDiTConfig(num_layers=0, num_single_layers=0).param_count()
     assert abs(one_double / 1e6 - 339.8) < 0.1 and abs(one_single / 1e6 - 141.6) < 0.1
+
+
+def test_condition_encode_follows_the_reference_class():
+    """train_flux/flux/condition.py:24-132: the reference's Condition class, compiled out of its file, and ours, over
+    the same fake `encode_images`: tokens, shifted position ids (`position_delta`, the "subject" default) and the
+    type-id column are equal; the type-id table is the reference's."""
+    import ast
+    from typing import List, Optional, Tuple, Union
+    from PIL import Image
+    from reflectionflow_b200 import pipeline as P
+    path = "/root/reference/train_flux/flux/condition.py"
+    assert P.condition_dict["cot"] == 12 and P.Condition.get_type_id("cot") == 12
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+
+    def fake_encode(pipe, image):
+        w, h = image.size
+        n = (w // 16) * (h // 16)
+        g = torch.Generator().manual_seed(w * 1000 + h)
+        ids = torch.zeros(n, 3)
+        ids[:, 1] = torch.arange(n) // (w // 16)
+        ids[:, 2] = torch.arange(n) % (w // 16)
+        return torch.randn(1, n, 64, generator=g), ids
+
+    ns = dict(torch=torch, Optional=Optional, Union=Union, List=List, Tuple=Tuple, Image=Image, FluxPipeline=object,
+              encode_images=fake_encode)
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.ClassDef) and node.name == "Condition" or \
+                isinstance(node, ast.Assign) and getattr(node.targets[0], "id", "") == "condition_dict":
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    assert ns["condition_dict"] == P.condition_dict
+
+    class Pipe:
+        device, dtype = "cpu", torch.float32
+
+        def encode_images(self, images, eps=None, generator=None):
+            return fake_encode(self, images)
+
+    # raw image -> condition image (condition.py:43-80), for the types that need no network model
+    import cv2  # noqa: F401 - used by the reference class through its module namespace
+    import numpy as np
+    from PIL import ImageFilter
+    ns.update(cv2=cv2, np=np, ImageFilter=ImageFilter)
+    raw = Image.fromarray((torch.rand(48, 80, 3, generator=torch.Generator().manual_seed(2)) * 255).to(torch.uint8).numpy())
+    for ctype in ("canny", "subject", "coloring", "deblurring", "fill", "cartoon"):
+        a = ns["Condition"](condition_type=ctype, raw_img=raw).condition
+        b = P.Condition(ctype, raw_img=raw).condition
+        assert a.mode == b.mode and a.size == b.size and a.tobytes() == b.tobytes(), ctype
+    with pytest.raises(NotImplementedError):
+        P.Condition("depth", raw_img=raw)
+    img = Image.new("RGB", (64, 32), (9, 9, 9))
+    for ctype, delta in (("cot", [0, -2]), ("cot", None), ("subject", None), ("canny", [3, 1])):
+        ref = ns["Condition"](condition_type=ctype, condition=img, position_delta=delta).encode(Pipe())
+        ours = P.Condition(ctype, condition=img, position_delta=delta).encode(Pipe())
+        for a, b in zip(ref, ours):
+            assert a.shape == b.shape and torch.equal(a.float(), b.float()), (ctype, delta)
