@@ -311,6 +311,9 @@ def tranformer_forward(transformer: B200FluxTransformer2DModel, condition_latent
     jak = params.get("joint_attention_kwargs")
     if jak is not None and jak.get("scale", 1.0) != 1.0:
         raise NotImplementedError("joint_attention_kwargs['scale'] != 1 is not supported")
+    if params.get("controlnet_block_samples") is not None or \
+            params.get("controlnet_single_block_samples") is not None:
+        raise NotImplementedError("controlnet residuals (transformer.py:26-27,182,226) are not on the tts path")
     cscale = float(getattr(transformer, "condition_scale", 1.0))
     out = transformer._forward(params["hidden_states"], params.get("encoder_hidden_states"),
                                params.get("pooled_projections"), params.get("timestep"),

@@ -411,3 +411,40 @@ def test_condition_encode_follows_the_reference_class():
         ours = P.Condition(ctype, condition=img, position_delta=delta).encode(Pipe())
         for a, b in zip(ref, ours):
             assert a.shape == b.shape and torch.equal(a.float(), b.float()), (ctype, delta)
+
+
+def test_tranformer_forward_takes_the_reference_parameter_names():
+    """transformer.py:18-44 `prepare_params`: every keyword the reference accepts is either consumed or refused loudly"""
+    import ast
+    import inspect
+    from reflectionflow_b200 import transformer as T
+    calls = []
+
+    class Fake:
+        condition_scale = 1.0
+
+        def _forward(self, *a):
+            calls.append(a)
+            return torch.zeros(1, 4, 64)
+
+    kw = dict(hidden_states=torch.zeros(1, 4, 64), encoder_hidden_states=1, pooled_projections=2, timestep=3, img_ids=4,
+              txt_ids=5, guidance=6, joint_attention_kwargs=None, controlnet_block_samples=None,
+              controlnet_single_block_samples=None)
+    out = T.tranformer_forward(Fake(), "cl", "ci", None, {"union_cond_attn": True}, 0, return_dict=False, **kw)
+    assert isinstance(out, tuple) and calls[0][1:7] == (1, 2, 3, 4, 5, 6) and calls[0][7:9] == ("cl", "ci")
+    assert hasattr(T.tranformer_forward(Fake(), None, None, None, **kw), "sample")
+    for bad in (dict(controlnet_block_samples=[0]), dict(controlnet_single_block_samples=[0]),
+                dict(joint_attention_kwargs={"scale": 0.5})):
+        with pytest.raises(NotImplementedError):
+            T.tranformer_forward(Fake(), None, None, None, **dict(kw, **bad))
+    with pytest.raises(NotImplementedError):
+        T.tranformer_forward(Fake(), None, None, None, {}, 1, **kw)
+    path = "/root/reference/train_flux/flux/transformer.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    from typing import Any, Dict, Optional
+    ns = dict(torch=torch, Optional=Optional, Dict=Dict, Any=Any)
+    fn = next(n for n in ast.parse(open(path).read()).body if isinstance(n, ast.FunctionDef) and n.name == "prepare_params")
+    exec(compile(ast.Module([fn], []), path, "exec"), ns)
+    names = [p for p in inspect.signature(ns["prepare_params"]).parameters if p != "kwargs"]
+    assert set(names) == set(kw) | {"return_dict"}
