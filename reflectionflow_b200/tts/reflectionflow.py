@@ -491,18 +491,32 @@ def main(argv=None, ctx: Optional[DistCtx] = None):
 
 
 def load_round0(paths: List[str], ctx: DistCtx) -> List[Candidate]:
-    """Round-0 candidates written by the noise-scaling stage: `<k>_round@<seed>.latent.pt` (or PNGs
-    once a VAE is attached — decoding them back needs the VAE encoder)."""
-    cands = []
+    """Round-0 candidates of the noise-scaling stage, in name order like the reference's listing
+    (tts_reflectionflow.py:537-547): `<k>_round@<seed>.latent.pt` as written by this framework (packed final latent,
+    decoded on demand), or — a stage-0 directory produced by the REFERENCE — plain `<k>_round@<seed>.png` files,
+    loaded as pixels (round-0 images are only scored and turned into condition images, never denoised further, so no
+    latent is needed; verifiers that score latents cannot be used on them)."""
+    stems = {}
     for p in paths:
-        if not p.endswith(".latent.pt"):
-            continue
-        stem = os.path.basename(p)[: -len(".latent.pt")]
-        seed = int(stem.split("@")[-1]) if "@" in stem else 0
-        lat = torch.load(p, map_location="cpu").to(ctx.device)
-        cands.append(Candidate(os.path.splitext(p)[0][: -len(".latent")] + ".png", seed, latents=lat))
+        if p.endswith(".latent.pt"):
+            stems.setdefault(p[: -len(".latent.pt")], {})["lat"] = p
+        elif p.endswith(".png"):
+            stems.setdefault(p[:-4], {})["png"] = p
+    cands = []
+    for stem in sorted(stems, key=lambda s: s + ".png"):
+        name = os.path.basename(stem)
+        seed = int(name.split("@")[-1]) if "@" in name and name.split("@")[-1].isdigit() else 0
+        if "lat" in stems[stem]:
+            lat = torch.load(stems[stem]["lat"], map_location="cpu").to(ctx.device)
+            cands.append(Candidate(stem + ".png", seed, latents=lat))
+        else:
+            import numpy as np
+            from PIL import Image
+            with Image.open(stems[stem]["png"]) as im:
+                u8 = torch.from_numpy(np.array(im.convert("RGB"))).to(ctx.device)
+            cands.append(Candidate(stem + ".png", seed, image_u8=u8))
     if not cands:
-        raise RuntimeError("no round-0 candidates (*.latent.pt) found under --imgpath")
+        raise RuntimeError("no round-0 candidates (*.latent.pt or *.png) found under --imgpath")
     return cands
 
 

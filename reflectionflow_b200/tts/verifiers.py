@@ -74,6 +74,11 @@ class StubVerifier:
     def value(self, cand: Candidate) -> float:
         if cand.stub_score is not None:
             return float(cand.stub_score)
+        if cand.latents is None:  # pixel-only candidate (a stage-0 PNG written by the reference): same kind of
+            if cand.image_u8 is None:  # fixed functional, of the image
+                raise RuntimeError(f"{cand.name}: neither latents nor pixels to score")
+            px = cand.image_u8.to(torch.float64)
+            return float((px.mean() / 255.0 - 0.5) * 0.1 + (px[::7, ::5].mean() - px[::5, ::7].mean()) / 2550.0)
         return latent_functional(cand.latents)
 
     def score_one(self, cand: Candidate, prompt: str) -> Dict[str, Any]:

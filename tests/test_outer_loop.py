@@ -272,3 +272,46 @@ def test_image_consuming_hooks_get_pixels_of_latent_only_parents(tmp_path, monke
                for _, m in client.create_calls)
     assert len(dp["reflections"]) == branch and dp["reflections"][0].startswith("[REFLEX] Original prompt: a cat")
     assert dp["refined_prompt"][0].startswith("[REFINE] Original prompt: a cat")
+
+
+def test_round0_from_a_reference_written_png_directory(tmp_path):
+    """A stage-0 directory produced by the REFERENCE holds `samples/<k>_round@<seed>.png` only.  `load_round0` takes
+    those as pixel-only candidates (name order, like the reference's listing); they can be scored and turned into
+    conditions, and a directory written by this framework (PNG + packed latent) still loads the latents."""
+    from PIL import Image
+    samples = tmp_path / "samples"
+    os.makedirs(samples)
+    g = torch.Generator().manual_seed(4)
+    seeds = [907, 15, 15002]
+    for s in seeds:
+        px = (torch.rand(16, 16, 3, generator=g) * 255).to(torch.uint8).numpy()
+        Image.fromarray(px).save(samples / f"1_round@{s}.png")
+    paths = sorted(str(samples / f) for f in os.listdir(samples))
+    cands = RF.load_round0(paths, DistCtx())
+    assert [c.seed for c in cands] == [15, 15002, 907] and all(c.latents is None and c.image_u8 is not None
+                                                               for c in cands)
+    assert [os.path.basename(c.name) for c in cands] == sorted(os.path.basename(p) for p in paths)
+    outs = StubVerifier("nvila").score(cands, ["p"] * 3)
+    assert len({o["score"] for o in outs}) == 3 and all(o["label"] in ("yes", "no") for o in outs)
+
+    def pixel_condition(pipe, parent, height, width, cond_size, seed):
+        from reflectionflow_b200.pipeline import Condition
+        v = parent.image_u8.float().mean() / 255.0
+        return Condition("cot", latents=torch.full((1, (cond_size // 16) ** 2, 64), float(v)).to(torch.bfloat16),
+                         position_delta=[0, -cond_size // 16])
+
+    dirs = {k: str(tmp_path / k) for k in ("last", "best", "bestround", "mid")}
+    for d in dirs.values():
+        os.makedirs(d)
+    torch.manual_seed(0)
+    dp = RF.sample(get_noises(S.MAX_SEED, 3, H, W), "a cat", ["a cat"] * 3, [""] * 3, 1, FakePipe(), 3, str(tmp_path),
+                   dict(CONFIG, search_args={"search_branch": 3, "search_rounds": 2}), dirs["last"], dirs["best"],
+                   dirs["bestround"], cands, dirs["mid"], 2, {}, verifier=StubVerifier("nvila"),
+                   reflector=StubReflector(), ctx=DistCtx(), generate_fn=fake_generate, condition_fn=pixel_condition)
+    assert len(dp["generated"]) == 3 and sorted(dp["topk_idx"]) == [0, 1, 2]
+    # this framework's own stage-0 output: the latent next to the PNG wins
+    torch.save(torch.randn(1, 16, 64).to(torch.bfloat16), samples / "1_round@15.latent.pt")
+    again = RF.load_round0(sorted(str(samples / f) for f in os.listdir(samples)), DistCtx())
+    assert [c.latents is not None for c in again] == [True, False, False] and len(again) == 3
+    with pytest.raises(RuntimeError, match="no round-0"):
+        RF.load_round0([str(tmp_path / "metadata.jsonl")], DistCtx())
