@@ -293,3 +293,42 @@ def test_reflection_generator_messages_equal_the_reference_function():
             exec(compile(ast.Module([node], []), path, "exec"), ns)
     for img, prompt in (("out/00001/midimg/2_round@17.png", 'a "quoted" prompt'), ("data:image/jpeg;base64,AAAA", "x")):
         assert V.ReflectionGeneratorOurs.generate_messages(img, prompt) == ns["generate_messages"](img, prompt)
+
+
+def test_image_verifier_adapter_over_the_reference_reward_method():
+    """reward_modeling/inference.py:71-76,155-180: the reference's `reward()` and `_norm()` methods, compiled out of
+    the class and bound to a fake inferencer (model -> logits, no tokenizer / checkpoint), behind `ImageVerifierOurs`:
+    the adapter consumes exactly what the reference method returns, batch by batch, and ranks by `Overall` descending."""
+    import ast
+    path = "/root/reference/reward_modeling/inference.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    ns = {}
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.ClassDef):
+            for m in node.body:
+                if isinstance(m, ast.FunctionDef) and m.name in ("reward", "_norm"):
+                    exec(compile(ast.Module([m], []), path, "exec"), ns)
+    assert {"reward", "_norm"} <= set(ns)
+    batches = []
+
+    class Inferencer:
+        inference_config = {"VQ_mean": 2.0, "VQ_std": 4.0}
+        reward = ns["reward"]
+        _norm = ns["_norm"]
+
+        def prepare_batch(self, image_paths, prompts, max_pixels):
+            batches.append(len(image_paths))
+            return {"pix": [im.getpixel((0, 0))[0] for im in image_paths]}
+
+        def model(self, return_dict, pix):
+            return {"logits": torch.tensor([[float(p)] for p in pix])}
+
+    cands = [_cand(i, (10 * i % 256, 0, 0)) for i in (5, 1, 9, 3, 7)]
+    v = V.ImageVerifierOurs(Inferencer(), batch_size=2)
+    out = v.score(cands, ["p"] * 5)
+    assert batches == [2, 2, 1]
+    assert [o["Overall"] for o in out] == [(10 * i - 2.0) / 4.0 for i in (5, 1, 9, 3, 7)]
+    assert all(o["VQ"] == o["Overall"] for o in out)
+    ranked = S.sort_outputs(out, "ours", "Overall")
+    assert [o["image_name"] for o in ranked] == [cands[k].name for k in (2, 4, 0, 3, 1)]
