@@ -218,3 +218,30 @@ def test_main_writes_the_reference_layout(tmp_path, monkeypatch):
         lines = open(out / d / "best_img_meta.jsonl").read().strip().splitlines()
         assert [ln.split(":")[0] for ln in lines] == ["refined_prompt1", "refined_prompt2"]
         assert all(m["prompt"] in p for p in json.loads(lines[0].split(": ", 1)[1]))
+
+
+@pytest.mark.parametrize("cfg_name", ["flux.1_dev_nvilascore.json", "flux.1_dev_gptscore.json"])
+def test_main_runs_on_the_reference_config_files_unchanged(tmp_path, monkeypatch, cfg_name):
+    """the reference's own tts/configs/*.json (1024x1024, 16 rounds x 2 candidates) drive main() as they are"""
+    ref_cfg = os.path.join("/root/reference/tts/configs", cfg_name)
+    if not os.path.exists(ref_cfg):
+        pytest.skip("reference tree not present")
+
+    class AnySizePipe:
+        vae = None
+
+        def __call__(self, prompt=None, latents=None, output_type="pil", **kw):
+            assert output_type == "latent" and latents.shape[1:] == (4096, 64) and kw["height"] == kw["width"] == 1024
+            return FluxPipelineOutput(images=(latents.float() * 0.5).to(torch.bfloat16))
+
+    monkeypatch.setattr(NP, "build_pipeline", lambda config, args, ctx: AnySizePipe())
+    (tmp_path / "meta.jsonl").write_text(json.dumps({"prompt": "a photo of a clock", "tag": "single_object"}) + "\n")
+    out = tmp_path / "out"
+    assert NP.main(["--pipeline_config_path", ref_cfg, "--meta_path", str(tmp_path / "meta.jsonl"), "--output_dir",
+                    str(out), "--synthetic", "--seed", "3"], ctx=DistCtx()) == 0
+    cfg = json.load(open(ref_cfg))
+    rounds, branch = cfg["search_args"]["search_rounds"], cfg["search_args"]["search_branch"]
+    files = os.listdir(out / "00000" / "samples")
+    assert len(files) == rounds * branch and {int(f.split("_round@")[0]) for f in files} == set(range(1, rounds + 1))
+    lines = open(out / "00000" / "best_img_meta.jsonl").read().strip().splitlines()
+    assert len(lines) == rounds and lines[-1].startswith(f"refined_prompt{rounds}: ")
