@@ -403,9 +403,12 @@ def synthetic_lora(cfg, rank: int = 32, seed: int = 1):
 
 
 @torch.no_grad()
-def main(argv=None, ctx: Optional[DistCtx] = None):
+def main(argv=None, ctx: Optional[DistCtx] = None, *, verifier=None, reflector=None,
+         generate_fn: Optional[Callable] = None, condition_fn: Optional[Callable] = None):
     """tts_reflectionflow.py:466-629.  `--imgpath` holds the round-0 candidates written by the
-    noise-scaling stage (NNNNN/{metadata.jsonl, samples/*}); each rank owns a share of every round."""
+    noise-scaling stage (NNNNN/{metadata.jsonl, samples/*}); each rank owns a share of every round.
+    `verifier` / `reflector` inject the external models (default: what the config names, stubs with --synthetic);
+    `generate_fn` / `condition_fn` replace the denoiser and the parent -> condition step (tests)."""
     args = parse_cli_args(argv)
     with open(args.pipeline_config_path, "r") as f:
         config = json.load(f)
@@ -424,9 +427,14 @@ def main(argv=None, ctx: Optional[DistCtx] = None):
     pipe = build_pipeline(config, args, ctx)
     verifier_args = config["verifier_args"]
     verifier_name = verifier_args.get("name", "openai")
-    verifier = load_verifier(verifier_args, args.synthetic,
-                             config["refine_args"].get("choice_of_metric", "overall_score"))
-    reflector = StubReflector()
+    verifier = verifier or load_verifier(verifier_args, args.synthetic,
+                                         config["refine_args"].get("choice_of_metric", "overall_score"))
+    reflector = reflector or StubReflector()
+    hooks = {}
+    if generate_fn is not None:
+        hooks["generate_fn"] = generate_fn
+    if condition_fn is not None:
+        hooks["condition_fn"] = condition_fn
     use_reflection = (config.get("reflection_args") or {}).get("run_reflection", False)
     use_refine = (config.get("prompt_refiner_args") or {}).get("run_refinement", False)
 
@@ -476,7 +484,7 @@ def main(argv=None, ctx: Optional[DistCtx] = None):
                         sample_path_bestround=dirs["samples_path_bestround"],
                         imagetoupdate=imagetoupdate, midimg_path=dirs["midimg"],
                         tag=meta0.get("tag"), total_rounds=search_rounds, chains=chains,
-                        verifier=verifier, reflector=reflector, ctx=ctx, defer_saves=True)
+                        verifier=verifier, reflector=reflector, ctx=ctx, defer_saves=True, **hooks)
             if use_reflection:
                 reflections = dp["reflections"]
             if use_refine:

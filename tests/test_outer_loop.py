@@ -315,3 +315,48 @@ def test_round0_from_a_reference_written_png_directory(tmp_path):
     assert [c.latents is not None for c in again] == [True, False, False] and len(again) == 3
     with pytest.raises(RuntimeError, match="no round-0"):
         RF.load_round0([str(tmp_path / "metadata.jsonl")], DistCtx())
+
+
+def test_main_on_the_reference_config_and_a_reference_written_stage0(tmp_path, monkeypatch):
+    """End to end on the host side: the reference's own `flux.1_dev_nvilascore.json` (1024x1024, condition 512, 16
+    rounds x 2 candidates) and a stage-0 directory as the REFERENCE writes it (metadata.jsonl + samples/*.png) drive
+    `reflectionflow.main`; denoiser and VAE are test-only fakes.  The artefact tree is the one `verifier_filter.py` and
+    the GenEval tooling read (tts_reflectionflow.py:562-579, 398-448)."""
+    from PIL import Image
+    ref_cfg = "/root/reference/tts/configs/flux.1_dev_nvilascore.json"
+    if not os.path.exists(ref_cfg):
+        pytest.skip("reference tree not present")
+    stage0 = tmp_path / "stage0" / "00000"
+    os.makedirs(stage0 / "samples")
+    (stage0 / "metadata.jsonl").write_text(json.dumps({"prompt": "a photo of a kite", "tag": "single_object"}))
+    g = torch.Generator().manual_seed(9)
+    for s in (11, 22):
+        Image.fromarray((torch.rand(32, 32, 3, generator=g) * 255).to(torch.uint8).numpy()).save(
+            stage0 / "samples" / f"1_round@{s}.png")
+    monkeypatch.setattr(RF, "build_pipeline", lambda config, args, ctx: FakePipe())
+
+    def pixel_or_latent_condition(pipe, parent, height, width, cond_size, seed):
+        from reflectionflow_b200.pipeline import Condition
+        assert (height, width, cond_size) == (1024, 1024, 512)
+        v = parent.image_u8.float().mean() / 255.0 if parent.latents is None else parent.latents.float().mean()
+        return Condition("cot", latents=torch.full((1, 1024, 64), float(v)).to(torch.bfloat16),
+                         position_delta=[0, -32])
+
+    out = tmp_path / "stage1"
+    rc = RF.main(["--pipeline_config_path", ref_cfg, "--imgpath", str(tmp_path / "stage0"), "--output_dir", str(out),
+                  "--synthetic", "--seed", "5"], ctx=DistCtx(), generate_fn=fake_generate,
+                 condition_fn=pixel_or_latent_condition)
+    assert rc == 0
+    cfg = json.load(open(ref_cfg))
+    rounds, branch = cfg["search_args"]["search_rounds"], cfg["search_args"]["search_branch"]
+    root = out / "00000"
+    assert json.load(open(root / "metadata.jsonl"))["prompt"] == "a photo of a kite"
+    mid = os.listdir(root / "midimg")
+    assert len(mid) == rounds * branch and {int(f.split("_round@")[0]) for f in mid} == set(range(1, rounds + 1))
+    assert len(os.listdir(root / "samples_lastround")) == branch
+    assert len(os.listdir(root / "samples_path_bestround")) == branch and len(os.listdir(root / "samples_best")) == 1
+    meta = open(root / "best_img_meta.jsonl").read().strip().splitlines()
+    assert sum(ln.startswith("reflections") for ln in meta) == rounds
+    assert sum(ln.startswith("refined_prompt") for ln in meta) == rounds
+    assert sum(ln.startswith("filenames_batch") for ln in meta) == rounds
+    assert len(open(root / "best_img_detailedscore.jsonl").read().strip().splitlines()) == rounds
