@@ -115,8 +115,9 @@ def sample(noises: Dict[int, torch.Tensor], original_prompt: str, updated_prompt
 
 
 @torch.no_grad()
-def main(argv=None, ctx: Optional[DistCtx] = None):
-    """tts_t2i_noise_prompt_scaling.py:149-248 (output layout NNNNN/{metadata.jsonl, samples/, best_img_meta.jsonl})."""
+def main(argv=None, ctx: Optional[DistCtx] = None, *, verifier=None, refiner=None):
+    """tts_t2i_noise_prompt_scaling.py:149-248 (output layout NNNNN/{metadata.jsonl, samples/, best_img_meta.jsonl}).
+    `verifier` / `refiner` inject the external models (default: the config's verifier, the offline stub refiner)."""
     args = parse_cli_args(argv)
     with open(args.pipeline_config_path, "r") as f:
         config = json.load(f)
@@ -136,9 +137,9 @@ def main(argv=None, ctx: Optional[DistCtx] = None):
     cfg_noload = dict(config)
     cfg_noload["pipeline_args"] = dict(config["pipeline_args"], lora_path=None)  # entry A: no LoRA
     pipe = build_pipeline(cfg_noload, args, ctx)
-    verifier = load_verifier(config["verifier_args"], args.synthetic,
-                             config["refine_args"].get("choice_of_metric", "overall_score"))
-    refiner = StubReflector()  # an OpenAIShapedReflector(client, ...) when a client is available
+    verifier = verifier or load_verifier(config["verifier_args"], args.synthetic,
+                                         config["refine_args"].get("choice_of_metric", "overall_score"))
+    refiner = refiner or StubReflector()  # an OpenAIShapedReflector(client, ...) when a client is available
     with open(args.meta_path) as fp:
         metadatas = [json.loads(line) for line in fp]
     metadatas = metadatas[args.start_index:] if args.end_index == -1 else \
